@@ -1,0 +1,876 @@
+// mapc.cu -- C ABI (include/mapc.h) and the Compute component behind it.
+//
+// Replaces Particles/Compute.{h,cpp} of the reference for the simulation path: the D3D12 compute
+// queue, command lists, root signature / PSO, descriptor heap and cross-adapter heap become CUDA
+// streams and device buffers; ID3D12Fence becomes mapc_fence (a 64-bit word every device and the
+// host can signal / wait on); the D3D12GpuTimer becomes cudaEvent pairs with the same 20-sample
+// moving average.  There is deliberately NO CPU fallback: without a CUDA device every entry
+// point that needs one returns MAPC_ERR_NO_DEVICE / MAPC_ERR_CUDA.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // declarations only: libnccl is dlopen()ed when a sharded handle is created
+#include <sched.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mapc.h"
+#include "nbody_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+mapc_status fail(mapc_status st, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return st;
+}
+
+#define MAPC_CUDA(expr)                                                                       \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            const mapc_status _st = (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver) \
+                                        ? MAPC_ERR_NO_DEVICE                                  \
+                                        : (_e == cudaErrorMemoryAllocation ? MAPC_ERR_OUT_OF_MEMORY \
+                                                                           : MAPC_ERR_CUDA);  \
+            return fail(_st, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                            \
+        }                                                                                     \
+    } while (0)
+
+#define MAPC_TRY(expr)                      \
+    do {                                    \
+        mapc_status _s = (expr);            \
+        if (_s != MAPC_OK) return _s;       \
+    } while (0)
+
+// ---- driver entry points for stream memory operations (no link-time libcuda dependency) -----
+typedef CUresult (*pfn_stream_value64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+pfn_stream_value64 g_write64 = nullptr, g_wait64 = nullptr;
+
+mapc_status load_stream_memops()
+{
+    if (g_write64 && g_wait64) return MAPC_OK;
+    void *w = nullptr, *q = nullptr;
+    cudaDriverEntryPointQueryResult r1, r2;
+    MAPC_CUDA(cudaGetDriverEntryPoint("cuStreamWriteValue64", &w, cudaEnableDefault, &r1));
+    MAPC_CUDA(cudaGetDriverEntryPoint("cuStreamWaitValue64", &q, cudaEnableDefault, &r2));
+    if (!w || !q || r1 != cudaDriverEntryPointSuccess || r2 != cudaDriverEntryPointSuccess)
+        return fail(MAPC_ERR_UNSUPPORTED, "driver lacks cuStreamWriteValue64/cuStreamWaitValue64");
+    g_write64 = (pfn_stream_value64)w;
+    g_wait64 = (pfn_stream_value64)q;
+    return MAPC_OK;
+}
+
+// ---- NCCL, loaded on demand ---------------------------------------------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+} g_nccl;
+
+mapc_status load_nccl()
+{
+    if (g_nccl.lib) return MAPC_OK;
+    const char *names[] = {getenv("MAPC_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *lib = nullptr;
+    for (const char *nm : names) {
+        if (!nm || !*nm) continue;
+        lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+        if (lib) break;
+    }
+    if (!lib) return fail(MAPC_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define MAPC_SYM(field, name)                                                         \
+    g_nccl.field = (decltype(g_nccl.field))dlsym(lib, name);                          \
+    if (!g_nccl.field) return fail(MAPC_ERR_NCCL, "libnccl lacks symbol %s", name)
+    MAPC_SYM(GetUniqueId, "ncclGetUniqueId");
+    MAPC_SYM(CommInitRank, "ncclCommInitRank");
+    MAPC_SYM(CommDestroy, "ncclCommDestroy");
+    MAPC_SYM(AllGather, "ncclAllGather");
+    MAPC_SYM(GetErrorString, "ncclGetErrorString");
+    MAPC_SYM(GetVersion, "ncclGetVersion");
+#undef MAPC_SYM
+    g_nccl.lib = lib;
+    return MAPC_OK;
+}
+
+#define MAPC_NCCL(expr)                                                                  \
+    do {                                                                                 \
+        ncclResult_t _r = (expr);                                                        \
+        if (_r != ncclSuccess)                                                           \
+            return fail(MAPC_ERR_NCCL, "%s failed: %s (%s:%d)", #expr,                   \
+                        g_nccl.GetErrorString(_r), __FILE__, __LINE__);                  \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+// ---- fence ----------------------------------------------------------------------------------
+struct mapc_fence {
+    volatile uint64_t *word = nullptr;  // pinned, portable, mapped; UVA: same address on devices
+};
+
+// ---- launch plan ------------------------------------------------------------------------------
+namespace {
+
+struct Plan {
+    int pairs;    // P: register pairs per thread (2P targets per thread)
+    int threads;  // T
+    int blocks_x;
+    int segments;
+};
+
+int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// Finer target blocks when there is little work so every SM gets several waves; the choice
+// changes neither the arithmetic nor its order (only S does), so it is free to vary.
+Plan make_plan(int n_targets, int n_sources, int sm_count)
+{
+    const int S = mapc_plan_segments((uint32_t)n_sources);
+    const int cand[5][2] = {{4, 256}, {4, 128}, {2, 128}, {1, 128}, {1, 64}};
+    Plan best{1, 64, 0, S};
+    const int fp = env_int("MAPC_PLAN_PAIRS", 0), ft = env_int("MAPC_PLAN_THREADS", 0);
+    for (int c = 0; c < 5; ++c) {
+        const int P = cand[c][0], T = cand[c][1];
+        const int per_block = T * 2 * P;
+        const int bx = (n_targets + per_block - 1) / per_block;
+        best = Plan{P, T, bx, S};
+        if (fp || ft) {
+            if ((!fp || fp == P) && (!ft || ft == T)) break;
+            continue;
+        }
+        if ((long long)bx * S >= 6LL * sm_count) break;
+    }
+    return best;
+}
+
+}  // namespace
+
+// ---- Compute ----------------------------------------------------------------------------------
+struct mapc_compute {
+    uint32_t n = 0;          // m_numParticles (global)
+    uint32_t i_first = 0;    // shard
+    uint32_t n_local = 0;
+    int device = 0;
+    int rank = 0, world = 1;
+    int sm_count = 148;
+    mapc_force_mode mode = MAPC_FORCE_ALLPAIRS;
+
+    cudaStream_t compute = nullptr;  // m_commandQueue (compute)
+    cudaStream_t comm = nullptr;     // all-gather stream
+    mapc_posvelo *posvelo[2] = {nullptr, nullptr};  // ping-pong sides, local shard
+    float4 *packed[2] = {nullptr, nullptr};         // packed positions, all N, per side
+    float4 *partial = nullptr;                      // [segments][n_local]
+    int partial_segments = 0;
+
+    mapc_fence *fence = nullptr;            // m_fence
+    mapc_fence *consumer_fence = nullptr;   // m_sharedRenderFence (borrowed)
+    uint64_t fence_value = 0;               // m_fenceValue
+    uint32_t buffer_index = 0;              // m_bufferIndex
+
+    ncclComm_t nccl = nullptr;
+    cudaEvent_t ev_integrated = nullptr;
+    cudaEvent_t ev_gathered[2] = {nullptr, nullptr};
+    bool gather_pending[2] = {false, false};
+
+    // "simulate ms" timer (Compute.cpp:445-446, D3D12GpuTimer.h:151-153)
+    static constexpr int kTimerSlots = 4;
+    static constexpr float kAverageOver = 20.f;
+    cudaEvent_t t_begin[kTimerSlots] = {}, t_end[kTimerSlots] = {};
+    bool t_pending[kTimerSlots] = {};
+    uint64_t t_next = 0, t_resolved = 0;
+    float ms_average = 0.f, ms_last = 0.f;
+    std::vector<float> step_log;  // raw samples not yet handed out by mapc_compute_step_times
+
+    uint64_t launches = 0;
+    bool has_state = false;
+};
+
+namespace {
+
+void resolve_timers(mapc_compute *c, bool block)
+{
+    while (c->t_resolved < c->t_next) {
+        const int slot = (int)(c->t_resolved % mapc_compute::kTimerSlots);
+        if (c->t_pending[slot]) {
+            if (block) cudaEventSynchronize(c->t_end[slot]);
+            else if (cudaEventQuery(c->t_end[slot]) != cudaSuccess) return;
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c->t_begin[slot], c->t_end[slot]) == cudaSuccess) {
+                // D3D12GpuTimer.h:151-153: t = (t*(N-1) + delta)/N
+                c->ms_average = (c->ms_average * (mapc_compute::kAverageOver - 1.f) + ms) /
+                                mapc_compute::kAverageOver;
+                c->ms_last = ms;
+                if (c->step_log.size() >= 4096) c->step_log.erase(c->step_log.begin());
+                c->step_log.push_back(ms);
+            }
+            c->t_pending[slot] = false;
+        }
+        ++c->t_resolved;
+    }
+}
+
+template <int P, int T>
+mapc_status launch_force(mapc_compute *c, const float4 *pos, int n_targets, int n_sources, int S,
+                         const mapc::SegList &segs, int blocks_x)
+{
+    if (segs.count == 0 || n_targets <= 0) return MAPC_OK;
+    dim3 grid((unsigned)blocks_x, (unsigned)segs.count, 1);
+    mapc::force_segments_kernel<P, T><<<grid, T, 0, c->compute>>>(
+        pos, c->partial, (int)c->i_first, n_targets, n_sources, S, segs, (int)c->n_local);
+    MAPC_CUDA(cudaGetLastError());
+    ++c->launches;
+    return MAPC_OK;
+}
+
+mapc_status launch_force_plan(mapc_compute *c, const Plan &pl, const float4 *pos, int n_targets,
+                              int n_sources, const mapc::SegList &segs)
+{
+    const int S = pl.segments;
+    if (pl.pairs == 4 && pl.threads == 256)
+        return launch_force<4, 256>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
+    if (pl.pairs == 4 && pl.threads == 128)
+        return launch_force<4, 128>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
+    if (pl.pairs == 2 && pl.threads == 128)
+        return launch_force<2, 128>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
+    if (pl.pairs == 1 && pl.threads == 128)
+        return launch_force<1, 128>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
+    return launch_force<1, 64>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
+}
+
+// targets of this shard that a Simulate(n_active) updates, as a count from i_first
+int local_targets(const mapc_compute *c, int n_active)
+{
+    if (n_active <= 0) return 0;
+    long long t = ((long long)n_active + MAPC_BLOCK_SIZE - 1) / MAPC_BLOCK_SIZE * MAPC_BLOCK_SIZE;
+    if (t > c->n) t = c->n;  // Dispatch(ceil(n/64)) (Compute.cpp:1041); OOB writes are dropped
+    long long loc = t - (long long)c->i_first;
+    if (loc < 0) loc = 0;
+    if (loc > c->n_local) loc = c->n_local;
+    return (int)loc;
+}
+
+mapc_status ensure_partial(mapc_compute *c, int segments)
+{
+    if (c->partial && c->partial_segments >= segments) return MAPC_OK;
+    if (c->partial) {
+        MAPC_CUDA(cudaStreamSynchronize(c->compute));
+        MAPC_CUDA(cudaFree(c->partial));
+        c->partial = nullptr;
+    }
+    MAPC_CUDA(cudaMalloc(&c->partial, (size_t)segments * c->n_local * sizeof(float4)));
+    c->partial_segments = segments;
+    return MAPC_OK;
+}
+
+mapc_status create_common(mapc_compute **out, uint32_t n, int device, int rank, int world,
+                          const void *nccl_id)
+{
+    if (!out) return fail(MAPC_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (n == 0) return fail(MAPC_ERR_INVALID_ARGUMENT, "num_particles must be > 0");
+    if (n > (1u << 28)) return fail(MAPC_ERR_INVALID_ARGUMENT, "num_particles too large");
+    if (world < 1 || rank < 0 || rank >= world)
+        return fail(MAPC_ERR_INVALID_ARGUMENT, "bad rank %d / world %d", rank, world);
+    if (n % (uint32_t)world != 0)
+        return fail(MAPC_ERR_INVALID_ARGUMENT, "num_particles %u not divisible by world %d", n, world);
+    int count = 0;
+    MAPC_CUDA(cudaGetDeviceCount(&count));
+    if (count <= 0) return fail(MAPC_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= count)
+        return fail(MAPC_ERR_INVALID_ARGUMENT, "device %d out of range (0..%d)", device, count - 1);
+    MAPC_CUDA(cudaSetDevice(device));
+    MAPC_TRY(load_stream_memops());
+
+    mapc_compute *c = new (std::nothrow) mapc_compute();
+    if (!c) return fail(MAPC_ERR_OUT_OF_MEMORY, "host allocation failed");
+    c->n = n;
+    c->device = device;
+    c->rank = rank;
+    c->world = world;
+    c->n_local = n / (uint32_t)world;
+    c->i_first = c->n_local * (uint32_t)rank;
+    mapc_status st = MAPC_OK;
+    auto body = [&]() -> mapc_status {
+        MAPC_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+        MAPC_CUDA(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+        MAPC_CUDA(cudaStreamCreateWithFlags(&c->comm, cudaStreamNonBlocking));
+        for (int s = 0; s < 2; ++s) {
+            MAPC_CUDA(cudaMalloc(&c->posvelo[s], (size_t)c->n_local * sizeof(mapc_posvelo)));
+            MAPC_CUDA(cudaMalloc(&c->packed[s], (size_t)n * sizeof(float4)));
+            MAPC_CUDA(cudaEventCreateWithFlags(&c->ev_gathered[s], cudaEventDisableTiming));
+        }
+        MAPC_CUDA(cudaEventCreateWithFlags(&c->ev_integrated, cudaEventDisableTiming));
+        for (int k = 0; k < mapc_compute::kTimerSlots; ++k) {
+            MAPC_CUDA(cudaEventCreate(&c->t_begin[k]));
+            MAPC_CUDA(cudaEventCreate(&c->t_end[k]));
+        }
+        MAPC_TRY(ensure_partial(c, mapc_plan_segments(n)));
+        // Compute.cpp:434-436: fence created with value 0, m_fenceValue++ -> 1
+        MAPC_TRY(mapc_fence_create(&c->fence, c->fence_value));
+        c->fence_value++;
+        if (world > 1) {
+            if (!nccl_id) return fail(MAPC_ERR_INVALID_ARGUMENT, "nccl_unique_id is NULL");
+            MAPC_TRY(load_nccl());
+            ncclUniqueId id;
+            static_assert(sizeof(id) == MAPC_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+            memcpy(&id, nccl_id, sizeof(id));
+            MAPC_NCCL(g_nccl.CommInitRank(&c->nccl, world, id, rank));
+        }
+        return MAPC_OK;
+    };
+    st = body();
+    if (st != MAPC_OK) {
+        const std::string keep = g_last_error;
+        mapc_compute_destroy(c);
+        g_last_error = keep;
+        return st;
+    }
+    *out = c;
+    return MAPC_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *mapc_last_error(void) { return g_last_error.c_str(); }
+const char *mapc_version(void) { return "mapc 0.1 (sm_100a)"; }
+
+mapc_status mapc_device_count(int *count)
+{
+    if (!count) return fail(MAPC_ERR_INVALID_ARGUMENT, "count is NULL");
+    *count = 0;
+    MAPC_CUDA(cudaGetDeviceCount(count));
+    return MAPC_OK;
+}
+
+int mapc_plan_segments(uint32_t n_sources) { return n_sources >= 131072u ? 8 : 32; }
+
+// ---- fences ------------------------------------------------------------------------------------
+mapc_status mapc_fence_create(mapc_fence **out, uint64_t initial_value)
+{
+    if (!out) return fail(MAPC_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    void *p = nullptr;
+    MAPC_CUDA(cudaHostAlloc(&p, sizeof(uint64_t), cudaHostAllocPortable | cudaHostAllocMapped));
+    mapc_fence *f = new (std::nothrow) mapc_fence();
+    if (!f) {
+        cudaFreeHost(p);
+        return fail(MAPC_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+    f->word = (volatile uint64_t *)p;
+    *f->word = initial_value;
+    *out = f;
+    return MAPC_OK;
+}
+
+mapc_status mapc_fence_destroy(mapc_fence *f)
+{
+    if (!f) return MAPC_OK;
+    if (f->word) cudaFreeHost((void *)f->word);
+    delete f;
+    return MAPC_OK;
+}
+
+uint64_t mapc_fence_completed_value(const mapc_fence *f)
+{
+    return f ? __atomic_load_n((const uint64_t *)f->word, __ATOMIC_ACQUIRE) : 0;
+}
+
+mapc_status mapc_fence_signal_host(mapc_fence *f, uint64_t value)
+{
+    if (!f) return fail(MAPC_ERR_INVALID_ARGUMENT, "fence is NULL");
+    __atomic_store_n((uint64_t *)f->word, value, __ATOMIC_RELEASE);
+    return MAPC_OK;
+}
+
+mapc_status mapc_fence_wait_host(const mapc_fence *f, uint64_t value, int timeout_ms)
+{
+    if (!f) return fail(MAPC_ERR_INVALID_ARGUMENT, "fence is NULL");
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (mapc_fence_completed_value(f) < value) {
+        if (++spins > 64) sched_yield();
+        if (timeout_ms >= 0 && (spins & 0xff) == 0) {
+            const auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(
+                                std::chrono::steady_clock::now() - t0).count();
+            if (ms > timeout_ms)
+                return fail(MAPC_ERR_TIMEOUT, "fence wait for %llu timed out at %llu",
+                            (unsigned long long)value,
+                            (unsigned long long)mapc_fence_completed_value(f));
+        }
+    }
+    return MAPC_OK;
+}
+
+mapc_status mapc_fence_signal_stream(mapc_fence *f, void *cuda_stream, uint64_t value)
+{
+    if (!f) return fail(MAPC_ERR_INVALID_ARGUMENT, "fence is NULL");
+    MAPC_TRY(load_stream_memops());
+    const CUresult r = g_write64((CUstream)cuda_stream, (CUdeviceptr)(uintptr_t)f->word, value,
+                                 CU_STREAM_WRITE_VALUE_DEFAULT);
+    if (r != CUDA_SUCCESS) return fail(MAPC_ERR_CUDA, "cuStreamWriteValue64 failed: %d", (int)r);
+    return MAPC_OK;
+}
+
+mapc_status mapc_fence_wait_stream(const mapc_fence *f, void *cuda_stream, uint64_t value)
+{
+    if (!f) return fail(MAPC_ERR_INVALID_ARGUMENT, "fence is NULL");
+    MAPC_TRY(load_stream_memops());
+    const CUresult r = g_wait64((CUstream)cuda_stream, (CUdeviceptr)(uintptr_t)f->word, value,
+                                CU_STREAM_WAIT_VALUE_GEQ);
+    if (r != CUDA_SUCCESS) return fail(MAPC_ERR_CUDA, "cuStreamWaitValue64 failed: %d", (int)r);
+    return MAPC_OK;
+}
+
+// ---- create / destroy ------------------------------------------------------------------------
+mapc_status mapc_compute_create(mapc_compute **out, uint32_t num_particles, int device,
+                                mapc_compute *prev)
+{
+    MAPC_TRY(create_common(out, num_particles, device, 0, 1, nullptr));
+    if (prev) {
+        const mapc_status st = mapc_compute_copy_state(*out, prev);  // Compute.cpp:88-91
+        if (st != MAPC_OK) {
+            const std::string keep = g_last_error;
+            mapc_compute_destroy(*out);
+            *out = nullptr;
+            g_last_error = keep;
+            return st;
+        }
+    }
+    return mapc_compute_wait_for_gpu(*out);  // Compute.cpp:97
+}
+
+mapc_status mapc_nccl_unique_id(void *out_id)
+{
+    if (!out_id) return fail(MAPC_ERR_INVALID_ARGUMENT, "out_id is NULL");
+    MAPC_TRY(load_nccl());
+    ncclUniqueId id;
+    MAPC_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(out_id, &id, sizeof(id));
+    return MAPC_OK;
+}
+
+mapc_status mapc_compute_create_sharded(mapc_compute **out, uint32_t num_particles, int device,
+                                        int rank, int world, const void *nccl_unique_id)
+{
+    MAPC_TRY(create_common(out, num_particles, device, rank, world, nccl_unique_id));
+    return mapc_compute_wait_for_gpu(*out);
+}
+
+mapc_status mapc_compute_destroy(mapc_compute *c)
+{
+    if (!c) return MAPC_OK;
+    DeviceGuard g(c->device);
+    // Compute::~Compute drains the queue first (Compute.cpp:104)
+    if (c->compute) cudaStreamSynchronize(c->compute);
+    if (c->comm) cudaStreamSynchronize(c->comm);
+    if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
+    for (int s = 0; s < 2; ++s) {
+        if (c->posvelo[s]) cudaFree(c->posvelo[s]);
+        if (c->packed[s]) cudaFree(c->packed[s]);
+        if (c->ev_gathered[s]) cudaEventDestroy(c->ev_gathered[s]);
+    }
+    if (c->partial) cudaFree(c->partial);
+    if (c->ev_integrated) cudaEventDestroy(c->ev_integrated);
+    for (int k = 0; k < mapc_compute::kTimerSlots; ++k) {
+        if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]);
+        if (c->t_end[k]) cudaEventDestroy(c->t_end[k]);
+    }
+    if (c->compute) cudaStreamDestroy(c->compute);
+    if (c->comm) cudaStreamDestroy(c->comm);
+    mapc_fence_destroy(c->fence);
+    delete c;
+    return MAPC_OK;
+}
+
+// ---- state in / out ---------------------------------------------------------------------------
+mapc_status mapc_compute_upload(mapc_compute *c, const mapc_posvelo *host, uint32_t n)
+{
+    if (!c || !host) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n != c->n) return fail(MAPC_ERR_INVALID_ARGUMENT, "upload of %u bodies into a handle of %u", n, c->n);
+    DeviceGuard g(c->device);
+    // stage all N bodies once (side 1's packed array is big enough only for positions, so use a
+    // temporary), then fan out: both PosVelo sides get the shard, both packed sides all N.
+    mapc_posvelo *tmp = nullptr;
+    MAPC_CUDA(cudaMalloc(&tmp, (size_t)n * sizeof(mapc_posvelo)));
+    mapc_status st = [&]() -> mapc_status {
+        MAPC_CUDA(cudaMemcpyAsync(tmp, host, (size_t)n * sizeof(mapc_posvelo), cudaMemcpyHostToDevice,
+                                  c->compute));
+        for (int s = 0; s < 2; ++s) {
+            MAPC_CUDA(cudaMemcpyAsync(c->posvelo[s], tmp + c->i_first,
+                                      (size_t)c->n_local * sizeof(mapc_posvelo),
+                                      cudaMemcpyDeviceToDevice, c->compute));
+            mapc::pack_positions_kernel<<<(n + 255) / 256, 256, 0, c->compute>>>(tmp, c->packed[s], (int)n);
+            MAPC_CUDA(cudaGetLastError());
+            ++c->launches;
+        }
+        c->gather_pending[0] = c->gather_pending[1] = false;
+        MAPC_CUDA(cudaStreamSynchronize(c->comm));
+        return MAPC_OK;
+    }();
+    if (st == MAPC_OK) st = mapc_compute_wait_for_gpu(c);  // Compute.cpp:922
+    cudaFree(tmp);
+    if (st == MAPC_OK) c->has_state = true;
+    return st;
+}
+
+mapc_status mapc_compute_download(mapc_compute *c, mapc_posvelo *host, uint32_t first, uint32_t count)
+{
+    if (!c || !host) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (first < c->i_first || (uint64_t)first + count > (uint64_t)c->i_first + c->n_local)
+        return fail(MAPC_ERR_INVALID_ARGUMENT, "range [%u, %u) outside shard [%u, %u)", first,
+                    first + count, c->i_first, c->i_first + c->n_local);
+    DeviceGuard g(c->device);
+    const uint32_t side = 1u - c->buffer_index;  // the side the last Simulate wrote
+    MAPC_CUDA(cudaMemcpyAsync(host, c->posvelo[side] + (first - c->i_first),
+                              (size_t)count * sizeof(mapc_posvelo), cudaMemcpyDeviceToHost, c->compute));
+    MAPC_CUDA(cudaStreamSynchronize(c->compute));
+    return MAPC_OK;
+}
+
+mapc_status mapc_compute_shard(const mapc_compute *c, uint32_t *first, uint32_t *count)
+{
+    if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (first) *first = c->i_first;
+    if (count) *count = c->n_local;
+    return MAPC_OK;
+}
+
+mapc_status mapc_compute_set_force_mode(mapc_compute *c, mapc_force_mode mode)
+{
+    if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (mode != MAPC_FORCE_ALLPAIRS && mode != MAPC_FORCE_WELL)
+        return fail(MAPC_ERR_INVALID_ARGUMENT, "unknown force mode %d", (int)mode);
+    c->mode = mode;
+    return MAPC_OK;
+}
+
+// ---- the step ---------------------------------------------------------------------------------
+mapc_status mapc_compute_simulate(mapc_compute *c, int num_active_particles, float delta_time,
+                                  float damping, uint64_t consumer_fence_value)
+{
+    if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (num_active_particles < 0 || (uint32_t)num_active_particles > c->n)
+        return fail(MAPC_ERR_INVALID_ARGUMENT, "num_active_particles %d outside [0, %u]",
+                    num_active_particles, c->n);
+    if (!c->has_state) return fail(MAPC_ERR_INVALID_ARGUMENT, "simulate before upload/init_particles");
+    DeviceGuard g(c->device);
+
+    // Compute.cpp:1012 -- "/previous/ copy must complete before overwriting the old state"
+    if (c->consumer_fence && consumer_fence_value > 0)
+        MAPC_TRY(mapc_fence_wait_stream(c->consumer_fence, c->compute, consumer_fence_value - 1));
+
+    const uint32_t b = c->buffer_index;  // write side; read side is 1-b
+    const uint32_t r = 1u - b;
+    const int n_targets = local_targets(c, num_active_particles);
+    const int n_sources = num_active_particles;
+
+    resolve_timers(c, false);
+    const int slot = (int)(c->t_next % mapc_compute::kTimerSlots);
+    if (c->t_pending[slot]) resolve_timers(c, true);
+    MAPC_CUDA(cudaEventRecord(c->t_begin[slot], c->compute));  // BeginTimer, Compute.cpp:1020
+
+    if (n_targets > 0) {
+        if (c->mode == MAPC_FORCE_WELL) {
+            mapc::well_step_kernel<<<(n_targets + 255) / 256, 256, 0, c->compute>>>(
+                c->posvelo[r], c->posvelo[b], c->packed[b], (int)c->i_first, n_targets, delta_time, damping);
+            MAPC_CUDA(cudaGetLastError());
+            ++c->launches;
+        } else {
+            const Plan pl = make_plan(n_targets, n_sources, c->sm_count);
+            MAPC_TRY(ensure_partial(c, pl.segments));
+            // segments whose sources all live in this shard are resident already (this rank wrote
+            // them in its own integrate pass); the others need the all-gather of side r.
+            mapc::SegList local{0, {}}, remote{0, {}};
+            for (int s = 0; s < pl.segments; ++s) {
+                int j0, j1;
+                mapc::segment_range(n_sources, pl.segments, s, j0, j1);
+                const bool is_local = c->world == 1 || !c->gather_pending[r] ||
+                                      (j0 >= (int)c->i_first && j1 <= (int)(c->i_first + c->n_local));
+                (is_local ? local : remote).ids[(is_local ? local : remote).count++] = s;
+            }
+            MAPC_TRY(launch_force_plan(c, pl, c->packed[r], n_targets, n_sources, local));
+            if (remote.count > 0) {
+                MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_gathered[r], 0));
+                MAPC_TRY(launch_force_plan(c, pl, c->packed[r], n_targets, n_sources, remote));
+            }
+            mapc::integrate_kernel<<<(n_targets + 255) / 256, 256, 0, c->compute>>>(
+                c->posvelo[r], c->posvelo[b], c->packed[b], c->partial, (int)c->n_local, pl.segments,
+                (int)c->i_first, n_targets, delta_time, damping);
+            MAPC_CUDA(cudaGetLastError());
+            ++c->launches;
+        }
+    }
+    MAPC_CUDA(cudaEventRecord(c->t_end[slot], c->compute));  // EndTimer, Compute.cpp:1046
+    c->t_pending[slot] = true;
+    ++c->t_next;
+
+    if (c->world > 1) {
+        // exchange step: every rank contributes its slice of the freshly written packed positions
+        if (c->gather_pending[r]) MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_gathered[r], 0));
+        MAPC_CUDA(cudaEventRecord(c->ev_integrated, c->compute));
+        MAPC_CUDA(cudaStreamWaitEvent(c->comm, c->ev_integrated, 0));
+        MAPC_NCCL(g_nccl.AllGather(c->packed[b] + c->i_first, c->packed[b], (size_t)c->n_local * 4,
+                                   ncclFloat, c->nccl, c->comm));
+        MAPC_CUDA(cudaEventRecord(c->ev_gathered[b], c->comm));
+        c->gather_pending[b] = true;
+    }
+
+    // MoveToNextFrame, Compute.cpp:993-1004
+    MAPC_TRY(mapc_fence_signal_stream(c->fence, c->compute, c->fence_value));
+    c->fence_value++;
+    c->buffer_index = 1u - c->buffer_index;
+    return MAPC_OK;
+}
+
+uint64_t mapc_compute_fence_value(const mapc_compute *c) { return c ? c->fence_value : 0; }
+
+mapc_status mapc_compute_wait_for_gpu(mapc_compute *c)
+{
+    if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
+    DeviceGuard g(c->device);
+    // Compute.cpp:931-938: Signal(m_fenceValue); m_fenceValue++; host wait
+    for (int s = 0; s < 2; ++s)
+        if (c->gather_pending[s]) MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_gathered[s], 0));
+    const uint64_t v = c->fence_value;
+    MAPC_TRY(mapc_fence_signal_stream(c->fence, c->compute, v));
+    c->fence_value++;
+    MAPC_CUDA(cudaStreamSynchronize(c->compute));
+    MAPC_CUDA(cudaStreamSynchronize(c->comm));
+    if (mapc_fence_completed_value(c->fence) < v)
+        return fail(MAPC_ERR_CUDA, "fence at %llu after drain, expected >= %llu",
+                    (unsigned long long)mapc_fence_completed_value(c->fence), (unsigned long long)v);
+    resolve_timers(c, true);
+    return MAPC_OK;
+}
+
+mapc_status mapc_compute_shared_handles(mapc_compute *c, mapc_fence *consumer_fence,
+                                        mapc_shared_handles *out)
+{
+    if (!c || !out) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
+    c->consumer_fence = consumer_fence;  // OpenSharedHandle(in_fenceHandle), Compute.cpp:946
+    for (int s = 0; s < 2; ++s) {
+        out->posvelo[s] = c->posvelo[s];
+        out->packed_pos[s] = c->packed[s];
+    }
+    out->fence = c->fence;
+    out->compute_stream = c->compute;
+    out->aligned_data_size = (uint64_t)c->n_local * sizeof(mapc_posvelo);
+    out->buffer_index = c->buffer_index;  // Compute.cpp:948
+    out->first_particle = c->i_first;
+    out->num_local = c->n_local;
+    out->device = c->device;
+    return MAPC_OK;
+}
+
+mapc_status mapc_compute_gpu_times(mapc_compute *c, float *ms_average, float *ms_last)
+{
+    if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
+    DeviceGuard g(c->device);
+    resolve_timers(c, false);
+    if (ms_average) *ms_average = c->ms_average;
+    if (ms_last) *ms_last = c->ms_last;
+    return MAPC_OK;
+}
+
+mapc_status mapc_compute_step_times(mapc_compute *c, float *ms_out, int capacity, int *count)
+{
+    if (!c || !count || (capacity > 0 && !ms_out)) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
+    DeviceGuard g(c->device);
+    resolve_timers(c, false);
+    int k = (int)c->step_log.size();
+    if (k > capacity) k = capacity < 0 ? 0 : capacity;
+    for (int i = 0; i < k; ++i) ms_out[i] = c->step_log[i];
+    c->step_log.erase(c->step_log.begin(), c->step_log.begin() + k);
+    *count = k;
+    return MAPC_OK;
+}
+
+mapc_status mapc_compute_flush(mapc_compute *c)
+{
+    if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
+    DeviceGuard g(c->device);
+    for (int s = 0; s < 2; ++s)
+        if (c->gather_pending[s]) MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_gathered[s], 0));
+    return MAPC_OK;
+}
+
+mapc_status mapc_compute_copy_state(mapc_compute *dst, mapc_compute *src)
+{
+    if (!dst || !src) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (dst->n != src->n || dst->i_first != src->i_first || dst->n_local != src->n_local)
+        return fail(MAPC_ERR_INVALID_ARGUMENT, "copy_state between different shapes (%u/%u vs %u/%u)",
+                    dst->n, dst->n_local, src->n, src->n_local);
+    if (!src->has_state) return fail(MAPC_ERR_INVALID_ARGUMENT, "source has no particle state");
+    MAPC_TRY(mapc_compute_wait_for_gpu(src));  // drained like Particles.cpp:467-471
+    MAPC_TRY(mapc_compute_wait_for_gpu(dst));
+    DeviceGuard g(dst->device);
+    for (int s = 0; s < 2; ++s) {
+        // positions and velocities of both sides (Compute.cpp:341-344, :395-398); the reference
+        // tunnels velocities through the shared position heap (:357-382), a peer copy needs no detour
+        MAPC_CUDA(cudaMemcpyPeerAsync(dst->posvelo[s], dst->device, src->posvelo[s], src->device,
+                                      (size_t)src->n_local * sizeof(mapc_posvelo), dst->compute));
+        MAPC_CUDA(cudaMemcpyPeerAsync(dst->packed[s], dst->device, src->packed[s], src->device,
+                                      (size_t)src->n * sizeof(float4), dst->compute));
+    }
+    // The reference restarts at m_bufferIndex 0 (Compute.cpp:80); carrying the index instead keeps
+    // the trajectory bit-exact across a migration (index 0 would re-read the older side half the time).
+    dst->buffer_index = src->buffer_index;
+    dst->mode = src->mode;
+    dst->gather_pending[0] = dst->gather_pending[1] = false;
+    dst->has_state = true;
+    return mapc_compute_wait_for_gpu(dst);  // Compute.cpp:409
+}
+
+uint64_t mapc_compute_kernel_launches(const mapc_compute *c) { return c ? c->launches : 0; }
+
+mapc_status mapc_compute_plan(const mapc_compute *c, int num_active_particles, int *pairs_per_thread,
+                              int *threads_per_block, int *num_blocks, int *segments)
+{
+    if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
+    const int n_targets = local_targets(c, num_active_particles);
+    const Plan pl = make_plan(n_targets, num_active_particles, c->sm_count);
+    if (pairs_per_thread) *pairs_per_thread = pl.pairs;
+    if (threads_per_block) *threads_per_block = pl.threads;
+    if (num_blocks) *num_blocks = pl.blocks_x * pl.segments;
+    if (segments) *segments = pl.segments;
+    return MAPC_OK;
+}
+
+mapc_status mapc_fp32_peak_probe(int device, int packed, float *tflops, float *ms_out)
+{
+    int count = 0;
+    MAPC_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(MAPC_ERR_INVALID_ARGUMENT, "device %d out of range", device);
+    DeviceGuard g(device);
+    int sms = 0;
+    MAPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    float *sink = nullptr;
+    MAPC_CUDA(cudaMalloc(&sink, 64));
+    cudaEvent_t e0, e1;
+    MAPC_CUDA(cudaEventCreate(&e0));
+    MAPC_CUDA(cudaEventCreate(&e1));
+    const int iters = 8192, blocks = sms * 8, threads = 256;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        MAPC_CUDA(cudaEventRecord(e0, 0));
+        if (packed) mapc::fp32_peak_kernel<true><<<blocks, threads>>>(sink, iters, 0.999f, 0.001f);
+        else mapc::fp32_peak_kernel<false><<<blocks, threads>>>(sink, iters, 0.999f, 0.001f);
+        MAPC_CUDA(cudaEventRecord(e1, 0));
+        MAPC_CUDA(cudaEventSynchronize(e1));
+        MAPC_CUDA(cudaGetLastError());
+        float ms = 0.f;
+        MAPC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    // 32 lane-FMAs per thread per iteration in both variants (16 x f32x2 or 32 scalar)
+    const double flops = 2.0 * 32.0 * iters * (double)blocks * threads;
+    if (tflops) *tflops = (float)(flops / (best * 1e-3) / 1e12);
+    if (ms_out) *ms_out = best;
+    return MAPC_OK;
+}
+
+// ---- initial conditions (InitializeParticles / LoadParticles) -----------------------------------
+namespace {
+
+// fast_rand(), Compute.cpp:605-609: g_seed = 214013*g_seed + 2531011; (g_seed >> 16) & 0x7FFF
+struct FastRand {
+    uint32_t state;
+    int next()
+    {
+        state = 214013u * state + 2531011u;
+        return (int)((state >> 16) & 0x7FFF);
+    }
+};
+
+// LoadParticles, USE_SCALAR_OPTIMIZED branch (Compute.cpp:719-749): random walk until |delta|^2 >= 10,
+// project on the shell of radius `spread` around `center`, velocity = cross(dir, perp) * speed with
+// dir = normalize(position), perp = normalize((1,1,1) - dir).  The reference's *Est normalisations
+// (rsqrtps, ~12 bit) are replaced by exact ones; its per-thread unseeded LCG by one seeded stream.
+void load_particles(mapc_posvelo *out, uint32_t count, float cx, float cy, float cz, float speed,
+                    float spread, FastRand &rng)
+{
+    const float k_scale = (1.f / 32767.f) * 2.f;  // (1/RAND_MAX)*2 with MSVC's RAND_MAX (Compute.cpp:721)
+    for (uint32_t i = 0; i < count; ++i) {
+        float dx = (float)rng.next() * k_scale - 1.f;
+        float dy = (float)rng.next() * k_scale - 1.f;
+        float dz = (float)rng.next() * k_scale - 1.f;
+        while (dx * dx + dy * dy + dz * dz < 10.f) {  // Compute.cpp:728
+            dx += (float)rng.next() * k_scale - 1.f;
+            dy += (float)rng.next() * k_scale - 1.f;
+            dz += (float)rng.next() * k_scale - 1.f;
+        }
+        const float inv = spread / sqrtf(dx * dx + dy * dy + dz * dz);
+        const float px = cx + dx * inv, py = cy + dy * inv, pz = cz + dz * inv;
+        const float il = 1.f / sqrtf(px * px + py * py + pz * pz);
+        const float ux = px * il, uy = py * il, uz = pz * il;           // direction (:746)
+        float qx = 1.f - ux, qy = 1.f - uy, qz = 1.f - uz;               // (1,1,1) - direction (:747)
+        const float iq = 1.f / sqrtf(qx * qx + qy * qy + qz * qz);
+        qx *= iq; qy *= iq; qz *= iq;
+        out[i].pos[0] = px; out[i].pos[1] = py; out[i].pos[2] = pz; out[i].pos[3] = 0.f;
+        out[i].velo[0] = (uy * qz - uz * qy) * speed;                    // cross(direction, perp) (:748)
+        out[i].velo[1] = (uz * qx - ux * qz) * speed;
+        out[i].velo[2] = (ux * qy - uy * qx) * speed;
+        out[i].velo[3] = 0.f;
+    }
+}
+
+}  // namespace
+
+mapc_status mapc_compute_init_particles(mapc_compute *c, uint32_t seed)
+{
+    if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
+    std::vector<mapc_posvelo> host(c->n);  // value-initialised like vector::resize (Compute.cpp:825-829)
+    memset(host.data(), 0, host.size() * sizeof(mapc_posvelo));
+    FastRand rng{seed};
+    // Compute.cpp:831-844: two groups of N/2 around x = +-0.75*ParticleSpread
+    const float center = MAPC_PARTICLE_SPREAD * 0.750f;
+    const uint32_t half = c->n / 2;
+    load_particles(host.data(), half, center, 0.f, 0.f, MAPC_INITIAL_PARTICLE_SPEED, MAPC_PARTICLE_SPREAD, rng);
+    load_particles(host.data() + half, half, -center, 0.f, 0.f, MAPC_INITIAL_PARTICLE_SPEED,
+                   MAPC_PARTICLE_SPREAD, rng);
+    return mapc_compute_upload(c, host.data(), c->n);
+}
+
+}  // extern "C"

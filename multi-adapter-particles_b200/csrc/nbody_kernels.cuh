@@ -1,0 +1,301 @@
+// nbody_kernels.cuh -- sm_100a kernels of the n-body step.
+//
+// What they reproduce (paths relative to the reference checkout):
+//   bodyBodyInteraction   Particles/nBodyGravityCS.hlsl:44-57   -> pair_interaction()
+//   CSMain epilogue       Particles/nBodyGravityCS.hlsl:103-108 -> integrate_body()
+//   CSMain as shipped     Particles/nBodyGravityCS.hlsl:86-109  -> well_step_kernel
+//   constants             Particles/nBodyGravityCS.hlsl:37-38, Particles/defines.h:37
+//
+// Design (B200-first, not a translation of the HLSL):
+//  * The pair math runs on packed fp32 pairs (FADD2 / FFMA2 / FMUL2, PTX *.f32x2): one thread
+//    owns 2*P target bodies as P register pairs, so every FMA-pipe instruction advances two
+//    interactions and issue slots stop being the limit; the j body is a scalar-broadcast operand
+//    (SASS `R.F32`), so one LDS.128 per source body feeds 2*P interactions.
+//  * MUFU.RSQ (rsqrt.approx.ftz) replaces 1/sqrt: fxc lowers `1.0f/sqrt(x)` to `rsq` as well.
+//  * Sources are cut into S canonical segments (mapc_plan_segments); a block owns one
+//    (target block, segment) cell and writes one partial per target.  Partials are summed left
+//    to right by integrate_kernel, so the result does not depend on which launch / stream /
+//    GPU evaluated a segment, nor on P or the block size.
+//  * No tensor cores: the work is not a contraction (d^2 via a GEMM cancels catastrophically).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mapc.h"
+
+namespace mapc {
+
+constexpr int kTileBodies = 256;  // source bodies per shared-memory stage (4 reference tiles of 64)
+
+struct SegList {
+    int count;
+    int ids[MAPC_MAX_SEGMENTS];
+};
+
+// j range [j0, j1) of canonical segment s: tile-aligned (64 bodies, Particles/defines.h:37),
+// tiles = dimx of Particles/Compute.cpp:544.
+__host__ __device__ inline void segment_range(int n_sources, int S, int s, int &j0, int &j1)
+{
+    const long long tiles = (n_sources + MAPC_BLOCK_SIZE - 1) / MAPC_BLOCK_SIZE;
+    long long a = (tiles * s) / S * MAPC_BLOCK_SIZE;
+    long long b = (tiles * (s + 1)) / S * MAPC_BLOCK_SIZE;
+    if (a > n_sources) a = n_sources;
+    if (b > n_sources) b = n_sources;
+    j0 = (int)a;
+    j1 = (int)b;
+}
+
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Two bodyBodyInteraction calls (nBodyGravityCS.hlsl:44-57) at once: lanes .x/.y are two
+// target bodies, b is the source body.  Operation order per lane:
+//   r = bj - bi                      (:46)   FADD2
+//   distSqr = dot(r,r) + 25          (:48-49) 3 FFMA2, softening folded into the first
+//   invDist = rsqrt(distSqr)         (:51)   MUFU.RSQ x2
+//   invDistCube = (inv*inv)*inv      (:52)   2 FMUL2
+//   s = mass * invDistCube [* 1]     (:54)   FMUL2 (particles == 1 is an exact no-op)
+//   ai += r * s                      (:56)   3 FFMA2
+__device__ __forceinline__ void pair_interaction(const float4 b, const float2 nxi, const float2 nyi,
+                                                 const float2 nzi, float2 &ax, float2 &ay, float2 &az)
+{
+    const float2 dx = __fadd2_rn(make_float2(b.x, b.x), nxi);
+    const float2 dy = __fadd2_rn(make_float2(b.y, b.y), nyi);
+    const float2 dz = __fadd2_rn(make_float2(b.z, b.z), nzi);
+    float2 d2 = __ffma2_rn(dx, dx, make_float2(MAPC_SOFTENING_SQUARED, MAPC_SOFTENING_SQUARED));
+    d2 = __ffma2_rn(dy, dy, d2);
+    d2 = __ffma2_rn(dz, dz, d2);
+    float2 inv;
+    inv.x = rsqrt_approx(d2.x);
+    inv.y = rsqrt_approx(d2.y);
+    const float2 inv2 = __fmul2_rn(inv, inv);
+    const float2 inv3 = __fmul2_rn(inv2, inv);
+    const float2 s = __fmul2_rn(inv3, make_float2(MAPC_PARTICLE_MASS, MAPC_PARTICLE_MASS));
+    ax = __ffma2_rn(dx, s, ax);
+    ay = __ffma2_rn(dy, s, ay);
+    az = __ffma2_rn(dz, s, az);
+}
+
+// One block = T threads x 2P targets against one canonical segment of sources.
+//   pos            packed float4 positions, global indexing (targets and sources)
+//   partial        [S][partial_stride] float4, local target indexing
+//   i_first/i_cnt  local targets are bodies [i_first, i_first + i_cnt)
+template <int P, int T>
+__global__ void __launch_bounds__(T)
+force_segments_kernel(const float4 *__restrict__ pos, float4 *__restrict__ partial, int i_first,
+                      int i_cnt, int n_sources, int S, SegList segs, int partial_stride)
+{
+    constexpr int kLoads = kTileBodies / T;  // staging loads per thread per tile
+    static_assert(kTileBodies % T == 0, "tile must be a multiple of the block size");
+    __shared__ float4 tile[2][kTileBodies];
+
+    const int tid = threadIdx.x;
+    const int seg = segs.ids[blockIdx.y];
+    int j0, j1;
+    segment_range(n_sources, S, seg, j0, j1);
+
+    // targets: thread owns local bodies i_block + q*T + tid, q = 0..2P-1 (coalesced in q);
+    // pair p = (q = 2p, q = 2p+1).  Out-of-range lanes are clamped and never stored.
+    const int i_block = blockIdx.x * (T * 2 * P);
+    float2 nxi[P], nyi[P], nzi[P], ax[P], ay[P], az[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        int ia = i_block + (2 * p) * T + tid;
+        int ib = i_block + (2 * p + 1) * T + tid;
+        ia = ia < i_cnt ? ia : i_cnt - 1;
+        ib = ib < i_cnt ? ib : i_cnt - 1;
+        const float4 a = pos[i_first + ia];
+        const float4 b = pos[i_first + ib];
+        nxi[p] = make_float2(-a.x, -b.x);
+        nyi[p] = make_float2(-a.y, -b.y);
+        nzi[p] = make_float2(-a.z, -b.z);
+        ax[p] = ay[p] = az[p] = make_float2(0.f, 0.f);
+    }
+
+    const int n_tiles = (j1 - j0 + kTileBodies - 1) / kTileBodies;
+    float4 stage[kLoads];
+
+    // prologue: tile 0 -> smem buffer 0
+    if (n_tiles > 0) {
+#pragma unroll
+        for (int l = 0; l < kLoads; ++l) {
+            const int j = j0 + l * T + tid;
+            stage[l] = j < j1 ? pos[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int l = 0; l < kLoads; ++l) tile[0][l * T + tid] = stage[l];
+    }
+    __syncthreads();
+
+    for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        const int jt = j0 + t * kTileBodies;
+        const bool has_next = (t + 1) < n_tiles;
+        // prefetch the next tile into registers while this one is consumed
+        if (has_next) {
+#pragma unroll
+            for (int l = 0; l < kLoads; ++l) {
+                const int j = jt + kTileBodies + l * T + tid;
+                stage[l] = j < j1 ? pos[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        const int cnt = (j1 - jt) < kTileBodies ? (j1 - jt) : kTileBodies;
+        if (cnt == kTileBodies) {
+#pragma unroll 8
+            for (int j = 0; j < kTileBodies; ++j) {
+                const float4 b = tile[buf][j];
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+                    pair_interaction(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+            }
+        } else {
+            // ragged last tile of the segment: loop bounded at the real count, no phantom bodies
+#pragma unroll 2
+            for (int j = 0; j < cnt; ++j) {
+                const float4 b = tile[buf][j];
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+                    pair_interaction(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+            }
+        }
+        if (has_next) {
+#pragma unroll
+            for (int l = 0; l < kLoads; ++l) tile[buf ^ 1][l * T + tid] = stage[l];
+        }
+        __syncthreads();
+    }
+
+    float4 *out = partial + (size_t)seg * partial_stride;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const int ia = i_block + (2 * p) * T + tid;
+        const int ib = i_block + (2 * p + 1) * T + tid;
+        if (ia < i_cnt) out[ia] = make_float4(ax[p].x, ay[p].x, az[p].x, 0.f);
+        if (ib < i_cnt) out[ib] = make_float4(ax[p].y, ay[p].y, az[p].y, 0.f);
+    }
+}
+
+// nBodyGravityCS.hlsl:103-108 with the contractions pinned (the CPU oracle's MIRRORED flavour
+// uses the same fmaf placement):
+//   vel += accel*dt (:103) FFMA; vel *= damping (:104) FMUL; pos += vel*dt (:105) FFMA;
+//   pos.w = length(accel) (:107); velocity stored as a float3, .w = 0 (:108).
+__device__ __forceinline__ void integrate_body(const float4 pos_in, const float4 vel_in,
+                                               const float ax, const float ay, const float az,
+                                               const float dt, const float damping, float4 &pos_out,
+                                               float4 &vel_out)
+{
+    float vx = __fmaf_rn(ax, dt, vel_in.x);
+    float vy = __fmaf_rn(ay, dt, vel_in.y);
+    float vz = __fmaf_rn(az, dt, vel_in.z);
+    vx = __fmul_rn(vx, damping);
+    vy = __fmul_rn(vy, damping);
+    vz = __fmul_rn(vz, damping);
+    pos_out.x = __fmaf_rn(vx, dt, pos_in.x);
+    pos_out.y = __fmaf_rn(vy, dt, pos_in.y);
+    pos_out.z = __fmaf_rn(vz, dt, pos_in.z);
+    pos_out.w = __fsqrt_rn(__fmaf_rn(az, az, __fmaf_rn(ay, ay, __fmul_rn(ax, ax))));
+    vel_out = make_float4(vx, vy, vz, 0.f);
+}
+
+// Sum the S segment partials left to right, integrate, write side b and the packed mirror.
+//   in/out       local PosVelo sides (index 0 = body i_first)
+//   pos_next     packed float4 positions of the side being written, global indexing
+__global__ void __launch_bounds__(256)
+integrate_kernel(const mapc_posvelo *__restrict__ in, mapc_posvelo *__restrict__ out,
+                 float4 *__restrict__ pos_next, const float4 *__restrict__ partial,
+                 int partial_stride, int S, int i_first, int n_targets, float dt, float damping)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_targets) return;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int s = 0; s < S; ++s) {
+        const float4 p = partial[(size_t)s * partial_stride + i];
+        ax = __fadd_rn(ax, p.x);
+        ay = __fadd_rn(ay, p.y);
+        az = __fadd_rn(az, p.z);
+    }
+    const float4 *src = reinterpret_cast<const float4 *>(in + i);
+    const float4 pos_in = src[0];
+    const float4 vel_in = src[1];
+    float4 pos_out, vel_out;
+    integrate_body(pos_in, vel_in, ax, ay, az, dt, damping, pos_out, vel_out);
+    float4 *dst = reinterpret_cast<float4 *>(out + i);
+    dst[0] = pos_out;
+    dst[1] = vel_out;
+    pos_next[i_first + i] = pos_out;
+}
+
+// The step the reference actually dispatches (nBodyGravityCS.hlsl:86-109): one gravity well at
+// the origin, note invDist = -1/sqrt (:97).  ~25 flop against 64 B of traffic per body: HBM-bound.
+__global__ void __launch_bounds__(256)
+well_step_kernel(const mapc_posvelo *__restrict__ in, mapc_posvelo *__restrict__ out,
+                 float4 *__restrict__ pos_next, int i_first, int n_targets, float dt, float damping)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_targets) return;
+    const float4 *src = reinterpret_cast<const float4 *>(in + i);
+    const float4 pos_in = src[0];
+    const float4 vel_in = src[1];
+    float d2 = __fmaf_rn(pos_in.x, pos_in.x, MAPC_SOFTENING_SQUARED);
+    d2 = __fmaf_rn(pos_in.y, pos_in.y, d2);
+    d2 = __fmaf_rn(pos_in.z, pos_in.z, d2);
+    const float inv = -rsqrt_approx(d2);
+    const float inv3 = __fmul_rn(__fmul_rn(inv, inv), inv);
+    const float s = __fmul_rn(inv3, MAPC_PARTICLE_MASS);
+    const float ax = __fmul_rn(pos_in.x, s);
+    const float ay = __fmul_rn(pos_in.y, s);
+    const float az = __fmul_rn(pos_in.z, s);
+    float4 pos_out, vel_out;
+    integrate_body(pos_in, vel_in, ax, ay, az, dt, damping, pos_out, vel_out);
+    float4 *dst = reinterpret_cast<float4 *>(out + i);
+    dst[0] = pos_out;
+    dst[1] = vel_out;
+    pos_next[i_first + i] = pos_out;
+}
+
+// packed float4 position mirror from a PosVelo array (after upload / state copy)
+__global__ void __launch_bounds__(256)
+pack_positions_kernel(const mapc_posvelo *__restrict__ in, float4 *__restrict__ pos, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pos[i] = reinterpret_cast<const float4 *>(in + i)[0];
+}
+
+// FP32 roofline probe: 16 independent accumulator chains per thread, nothing but FMAs.
+template <bool PACKED>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float a, float b)
+{
+    if (PACKED) {
+        float2 acc[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] = make_float2(threadIdx.x * 1e-3f + k, k * 0.5f);
+        const float2 a2 = make_float2(a, a * 0.999f), b2 = make_float2(b, b * 1.001f);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] = __ffma2_rn(acc[k], a2, b2);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s += acc[k].x + acc[k].y;
+        if (s == 123.456f) out[0] = s;
+    } else {
+        float acc[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc[k] = threadIdx.x * 1e-3f + k;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc[k] = __fmaf_rn(acc[k], a, b);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s += acc[k];
+        if (s == 123.456f) out[0] = s;
+    }
+}
+
+}  // namespace mapc

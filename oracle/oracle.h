@@ -1,0 +1,95 @@
+/*
+ * oracle/oracle.h -- CPU restatement of the Multi-Adapter-Particles n-body step.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load it, and only as the checker / reported CPU baseline.
+ *
+ * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
+ * this path and its shader (HLSL cs_5_0 run by D3D12 on
+ * Windows, Particles/Compute.cpp:488-511) cannot execute here, so there is no
+ * reference output to pin this restatement against.  It is pinned instead by
+ * closed-form known-answer tests derived from Particles/nBodyGravityCS.hlsl:44-57
+ * and :86-109 (tests/test_oracle_kat.py) and by an fp64 direct sum.
+ *
+ * What it follows (all paths relative to /root/reference):
+ *   Particles/nBodyGravityCS.hlsl:37-38   softeningSquared = 25, g_fParticleMass = 70000
+ *   Particles/nBodyGravityCS.hlsl:44-57   bodyBodyInteraction (pair math, operation order)
+ *   Particles/nBodyGravityCS.hlsl:88-89   load pos / vel
+ *   Particles/nBodyGravityCS.hlsl:92-101  literal central-well acceleration (CSMain as shipped)
+ *   Particles/nBodyGravityCS.hlsl:103-108 kick, damp, drift, pos.w = length(accel)
+ *   Particles/Compute.cpp:542-546         N, dimx = ceil(N/64), dt = 0.1f, damping = 1.0f
+ *   Particles/Compute.cpp:1041            Dispatch(ceil(nActive/64)) -> which bodies are updated
+ *   Particles/defines.h:37                BLOCK_SIZE 64 (j tile)
+ *
+ * Summation shape (a build decision; the reference pins only "ascending j, tiles of 64"):
+ * the sources j in [0, n_sources) are cut into S contiguous, tile-aligned segments;
+ * inside a segment one fp32 accumulator per axis runs over ascending j; the S partials
+ * are then added left to right, ((p0 + p1) + p2) + ... + p(S-1).
+ */
+#ifndef MAPO_ORACLE_H
+#define MAPO_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { float pos[4]; float velo[4]; } mapo_posvelo; /* ParticleShared.hlsl:12-16 */
+
+#define MAPO_SOFTENING_SQUARED 25.0f   /* nBodyGravityCS.hlsl:37 */
+#define MAPO_PARTICLE_MASS     70000.0f /* nBodyGravityCS.hlsl:38 */
+#define MAPO_TILE              64      /* defines.h:37 */
+
+enum { MAPO_LITERAL = 0, MAPO_MIRRORED = 1 };
+
+/* dimx of Compute.cpp:544 */
+int  mapo_num_tiles(int n);
+/* canonical segment count for n sources: 8 when n >= 131072, else 32 */
+int  mapo_default_segments(int n);
+/* j range [j0, j1) of segment s out of S over n_sources sources */
+void mapo_segment_range(int n_sources, int S, int s, int *j0, int *j1);
+/* number of bodies one Simulate(n_active) updates: min(n, 64*ceil(n_active/64)) (Compute.cpp:1041) */
+int  mapo_num_targets(int n, int n_active);
+
+/* nBodyGravityCS.hlsl:44-57, written exactly as the shader is (separate mul/add, 1.0f/sqrtf). */
+void mapo_body_body_interaction(float ai[3], const float bj[4], const float bi[4],
+                                float mass, int particles);
+/* same pair with the contractions the CUDA kernel uses (explicit fmaf, softening folded
+ * into the first fma of the dot product); 1.0f/sqrtf stands in for MUFU.RSQ. */
+void mapo_body_body_interaction_mirrored(float ai[3], const float bj[4], const float bi[4],
+                                         float mass);
+
+/* accel of the listed targets (NULL = targets 0..n_targets-1) from sources [0, n_sources),
+ * canonical S-segment order, one scalar call of the pair function per (i, j). Slow; small N. */
+void mapo_accel_allpairs_scalar(const mapo_posvelo *in, int n_sources, int S, int flavour,
+                                const int *targets, int n_targets, float *accel3);
+/* same numbers (bit-identical), 8 targets per inner loop so gcc can vectorise across i;
+ * OpenMP over target blocks; threads <= 0 means omp_get_max_threads(). */
+void mapo_accel_allpairs(const mapo_posvelo *in, int n_sources, int S, int flavour,
+                         const int *targets, int n_targets, float *accel3, int threads);
+/* fp64 direct sum, ascending j, no segments -- reported alongside, never gating */
+void mapo_accel_fp64(const mapo_posvelo *in, int n_sources,
+                     const int *targets, int n_targets, double *accel3, int threads);
+
+/* nBodyGravityCS.hlsl:103-108 for one body */
+void mapo_integrate(const mapo_posvelo *in_i, const float accel[3], float dt, float damping,
+                    int flavour, mapo_posvelo *out_i);
+
+/* one all-pairs step: out[i] for i < mapo_num_targets(n, n_active) is written, the rest of
+ * out is left untouched (the stale side of the ping-pong, as in the reference). */
+void mapo_step_allpairs(const mapo_posvelo *in, mapo_posvelo *out, int n, int n_active,
+                        float dt, float damping, int S, int flavour, int threads);
+/* subsampled step: out_targets[k] is the new state of body targets[k] */
+void mapo_step_allpairs_targets(const mapo_posvelo *in, int n_sources,
+                                const int *targets, int n_targets, float dt, float damping,
+                                int S, int flavour, int threads, mapo_posvelo *out_targets);
+/* the step the reference actually executes: origin gravity well, nBodyGravityCS.hlsl:86-109 */
+void mapo_step_well(const mapo_posvelo *in, mapo_posvelo *out, int n, int n_active,
+                    float dt, float damping, int flavour);
+
+int  mapo_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,194 @@
+"""ctypes face of oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY (see oracle/oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  PARITY UNPINNED: the reference has no fixtures for this path; the oracle is
+pinned by closed-form KATs (tests/test_oracle_kat.py) and an fp64 direct sum.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, c_double, c_float, c_int, c_void_p
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle.so")
+
+LITERAL = 0
+MIRRORED = 1
+POSVELO_DTYPE = np.dtype([("pos", np.float32, 4), ("velo", np.float32, 4)])
+
+_lib = None
+
+
+def build() -> str:
+    res = subprocess.run(["make", "-C", HERE], capture_output=True, text=True)
+    if res.returncode != 0:
+        print(res.stdout, res.stderr)
+        raise RuntimeError("building liboracle.so failed")
+    return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    lib = ctypes.CDLL(LIB_PATH)
+    fp, ip, dp = POINTER(c_float), POINTER(c_int), POINTER(c_double)
+    lib.mapo_num_tiles.restype = c_int
+    lib.mapo_num_tiles.argtypes = [c_int]
+    lib.mapo_default_segments.restype = c_int
+    lib.mapo_default_segments.argtypes = [c_int]
+    lib.mapo_segment_range.restype = None
+    lib.mapo_segment_range.argtypes = [c_int, c_int, c_int, ip, ip]
+    lib.mapo_num_targets.restype = c_int
+    lib.mapo_num_targets.argtypes = [c_int, c_int]
+    lib.mapo_body_body_interaction.restype = None
+    lib.mapo_body_body_interaction.argtypes = [fp, fp, fp, c_float, c_int]
+    lib.mapo_body_body_interaction_mirrored.restype = None
+    lib.mapo_body_body_interaction_mirrored.argtypes = [fp, fp, fp, c_float]
+    lib.mapo_accel_allpairs_scalar.restype = None
+    lib.mapo_accel_allpairs_scalar.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
+    lib.mapo_accel_allpairs.restype = None
+    lib.mapo_accel_allpairs.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int]
+    lib.mapo_accel_fp64.restype = None
+    lib.mapo_accel_fp64.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int]
+    lib.mapo_integrate.restype = None
+    lib.mapo_integrate.argtypes = [c_void_p, fp, c_float, c_float, c_int, c_void_p]
+    lib.mapo_step_allpairs.restype = None
+    lib.mapo_step_allpairs.argtypes = [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int, c_int, c_int]
+    lib.mapo_step_allpairs_targets.restype = None
+    lib.mapo_step_allpairs_targets.argtypes = [c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_int,
+                                               c_int, c_int, c_void_p]
+    lib.mapo_step_well.restype = None
+    lib.mapo_step_well.argtypes = [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int]
+    lib.mapo_max_threads.restype = c_int
+    lib.mapo_max_threads.argtypes = []
+    _lib = lib
+    return lib
+
+
+def _pv(a) -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype != POSVELO_DTYPE:
+        a = np.ascontiguousarray(a, dtype=np.float32).view(POSVELO_DTYPE).reshape(-1)
+    return np.ascontiguousarray(a)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(c_void_p)
+
+
+def max_threads() -> int:
+    return int(load().mapo_max_threads())
+
+
+def default_segments(n: int) -> int:
+    return int(load().mapo_default_segments(n))
+
+
+def num_targets(n: int, n_active: int) -> int:
+    return int(load().mapo_num_targets(n, n_active))
+
+
+def segment_range(n_sources: int, S: int, s: int):
+    j0, j1 = c_int(0), c_int(0)
+    load().mapo_segment_range(n_sources, S, s, ctypes.byref(j0), ctypes.byref(j1))
+    return j0.value, j1.value
+
+
+def body_body_interaction(ai, bj, bi, mass=70000.0, particles=1, flavour=LITERAL):
+    """One call of bodyBodyInteraction (nBodyGravityCS.hlsl:44-57); returns the updated ai."""
+    a = np.array(ai, dtype=np.float32)
+    j = np.array(list(bj) + [0.0] * (4 - len(bj)), dtype=np.float32)
+    i = np.array(list(bi) + [0.0] * (4 - len(bi)), dtype=np.float32)
+    fp = POINTER(c_float)
+    if flavour == LITERAL:
+        load().mapo_body_body_interaction(a.ctypes.data_as(fp), j.ctypes.data_as(fp), i.ctypes.data_as(fp),
+                                          mass, particles)
+    else:
+        load().mapo_body_body_interaction_mirrored(a.ctypes.data_as(fp), j.ctypes.data_as(fp),
+                                                   i.ctypes.data_as(fp), mass)
+    return a
+
+
+def accel_allpairs(particles, n_sources=None, S=None, flavour=LITERAL, targets=None, threads=0,
+                   scalar=False) -> np.ndarray:
+    p = _pv(particles)
+    n_sources = p.shape[0] if n_sources is None else n_sources
+    S = default_segments(n_sources) if S is None else S
+    if targets is None:
+        t, nt, tp = None, p.shape[0], None
+    else:
+        t = np.ascontiguousarray(targets, dtype=np.int32)
+        nt, tp = t.shape[0], _ptr(t)
+    out = np.zeros((nt, 3), dtype=np.float32)
+    if scalar:
+        load().mapo_accel_allpairs_scalar(_ptr(p), n_sources, S, flavour, tp, nt, _ptr(out))
+    else:
+        load().mapo_accel_allpairs(_ptr(p), n_sources, S, flavour, tp, nt, _ptr(out), threads)
+    return out
+
+
+def accel_fp64(particles, n_sources=None, targets=None, threads=0) -> np.ndarray:
+    p = _pv(particles)
+    n_sources = p.shape[0] if n_sources is None else n_sources
+    if targets is None:
+        nt, tp = p.shape[0], None
+    else:
+        t = np.ascontiguousarray(targets, dtype=np.int32)
+        nt, tp = t.shape[0], _ptr(t)
+    out = np.zeros((nt, 3), dtype=np.float64)
+    load().mapo_accel_fp64(_ptr(p), n_sources, tp, nt, _ptr(out), threads)
+    return out
+
+
+def step_allpairs(particles, n_active=None, dt=0.1, damping=1.0, S=None, flavour=LITERAL, threads=0,
+                  out=None) -> np.ndarray:
+    """One all-pairs step.  `out` (the side being overwritten) defaults to a copy of the input."""
+    p = _pv(particles)
+    n = p.shape[0]
+    n_active = n if n_active is None else n_active
+    S = default_segments(min(n_active, n)) if S is None else S
+    o = p.copy() if out is None else out
+    load().mapo_step_allpairs(_ptr(p), _ptr(o), n, n_active, dt, damping, S, flavour, threads)
+    return o
+
+
+def step_allpairs_targets(particles, targets, n_sources=None, dt=0.1, damping=1.0, S=None, flavour=LITERAL,
+                          threads=0) -> np.ndarray:
+    p = _pv(particles)
+    n_sources = p.shape[0] if n_sources is None else n_sources
+    S = default_segments(n_sources) if S is None else S
+    t = np.ascontiguousarray(targets, dtype=np.int32)
+    o = np.zeros(t.shape[0], dtype=POSVELO_DTYPE)
+    load().mapo_step_allpairs_targets(_ptr(p), n_sources, _ptr(t), t.shape[0], dt, damping, S, flavour,
+                                      threads, _ptr(o))
+    return o
+
+
+def step_well(particles, n_active=None, dt=0.1, damping=1.0, flavour=LITERAL, out=None) -> np.ndarray:
+    p = _pv(particles)
+    n = p.shape[0]
+    n_active = n if n_active is None else n_active
+    o = p.copy() if out is None else out
+    load().mapo_step_well(_ptr(p), _ptr(o), n, n_active, dt, damping, flavour)
+    return o
+
+
+def rel_errors(got, ref) -> dict:
+    """Error metrics used by the parity tests (documented in DESIGN.md):
+    per quantity q in {pos.xyz, velo.xyz, pos.w}:  max_i |got_i - ref_i|_inf / max_i |ref_i|_inf."""
+    g, r = _pv(got), _pv(ref)
+    out = {}
+    for name, gq, rq in (("pos", g["pos"][:, :3], r["pos"][:, :3]),
+                         ("velo", g["velo"][:, :3], r["velo"][:, :3]),
+                         ("accel_len", g["pos"][:, 3:4], r["pos"][:, 3:4])):
+        num = np.abs(gq.astype(np.float64) - rq.astype(np.float64)).max() if gq.size else 0.0
+        den = np.abs(rq.astype(np.float64)).max() if rq.size else 0.0
+        out[name] = float(num / den) if den > 0 else float(num)
+    return out

@@ -1,0 +1,270 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): max relative error <= 1e-5 after one step and <= 1e-4
+after ten, against the LITERAL oracle flavour; the metric is oracle_py.rel_errors
+(max_i |got_i - ref_i|_inf / max_i |ref_i|_inf per quantity).  Against the MIRRORED flavour
+(same fma placement as the kernel, exact 1/sqrt instead of MUFU.RSQ) a tighter 3e-6 is asserted.
+"""
+import os
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_1 = 1e-5
+TOL_10 = 1e-4
+TOL_MIRRORED = 3e-6
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gentle_sphere(mapc, n, seed, speed=0.0):
+    # radius chosen so mass*N*dt^2/R^3 ~ 1e-3 ("tolerance vs chaos")
+    radius = max(100.0, 2000.0 * (n / 10_000.0) ** (1.0 / 3.0))
+    return mapc.ic.uniform_sphere(n, radius, seed, speed)
+
+
+def gpu_steps(mapc, particles, steps, n_active=None, dt=0.1, damping=1.0, mode=0):
+    n = particles.shape[0]
+    with mapc.Compute(n, 0) as c:
+        c.SetForceMode(mode)
+        c.Upload(particles)
+        for _ in range(steps):
+            c.Simulate(n if n_active is None else n_active, 0, dt, damping)
+        c.WaitForGpu()
+        return c.Download()
+
+
+def assert_close(oracle, got, ref, tol, what=""):
+    err = oracle.rel_errors(got, ref)
+    assert max(err.values()) <= tol, f"{what} rel errors {err} exceed {tol}"
+    return err
+
+
+@pytest.mark.parametrize("n", [64, 100, 1000, 4097, 10_000, 16_384])
+def test_allpairs_one_step(mapc, oracle, gpu, n):
+    p = gentle_sphere(mapc, n, seed=n, speed=1.0)
+    got = gpu_steps(mapc, p, 1)
+    assert_close(oracle, got, oracle.step_allpairs(p, flavour=oracle.LITERAL), TOL_1, f"n={n} literal")
+    assert_close(oracle, got, oracle.step_allpairs(p, flavour=oracle.MIRRORED), TOL_MIRRORED, f"n={n} mirrored")
+    assert np.all(got["velo"][:, 3] == 0.0)
+
+
+def test_allpairs_ten_steps_10k(mapc, oracle, gpu):
+    p = mapc.ic.workload("interactive_10k")
+    got = gpu_steps(mapc, p, 10)
+    ref = p
+    for _ in range(10):
+        ref = oracle.step_allpairs(ref)
+    assert_close(oracle, got, ref, TOL_10, "10 steps")
+
+
+@pytest.mark.parametrize("name", ["sphere_1000", "plummer_777"])
+def test_golden_allpairs(mapc, oracle, gpu, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    inp = g["input"].view(mapc.POSVELO_DTYPE).reshape(-1)
+    dt, damping, steps = float(g["dt"]), float(g["damping"]), int(g["steps"])
+    assert int(g["S"]) == mapc.plan_segments(inp.shape[0])
+    one = gpu_steps(mapc, inp, 1, dt=dt, damping=damping)
+    assert_close(oracle, one, g["literal_1"], TOL_1, name + " step 1")
+    last = gpu_steps(mapc, inp, steps, dt=dt, damping=damping)
+    assert_close(oracle, last, g["literal_last"], TOL_10, name + f" step {steps}")
+    # fp64 direct sum, reported alongside (not part of the stated tolerance, but must be sane)
+    acc_gpu = (one["velo"][:, :3].astype(np.float64) / damping - inp["velo"][:, :3]) / dt
+    scale = np.abs(g["accel_fp64"]).max()
+    assert np.abs(acc_gpu - g["accel_fp64"]).max() / scale < 1e-4
+
+
+def test_golden_well(mapc, oracle, gpu):
+    g = np.load(os.path.join(GOLDEN, "well_1000.npz"))
+    inp = g["input"].view(mapc.POSVELO_DTYPE).reshape(-1)
+    got = gpu_steps(mapc, inp, 1, mode=mapc.FORCE_WELL)
+    assert_close(oracle, got, g["literal_1"], 2e-6, "well")
+
+
+def test_well_mode_kat6(mapc, gpu):
+    # pos=(12,0,0), vel=0 -> accel=(-382.33955,0,0), vel'=(-38.233955,0,0), pos'=(8.1766045,0,0)
+    p = np.zeros(64, dtype=mapc.POSVELO_DTYPE)
+    p["pos"][:, 0] = 12.0
+    got = gpu_steps(mapc, p, 1, mode=mapc.FORCE_WELL)
+    a = 70000.0 * 12.0 / 2197.0
+    np.testing.assert_allclose(got["velo"][:, 0], -a * 0.1, rtol=1e-6)
+    np.testing.assert_allclose(got["pos"][:, 0], 12.0 - a * 0.01, rtol=1e-6)
+    np.testing.assert_allclose(got["pos"][:, 3], a, rtol=1e-6)
+
+
+def test_pair_kats_on_gpu(mapc, gpu):
+    # KAT 1 (12 apart), KAT 3/5 (coincident bodies -> exactly zero), via one all-pairs step
+    p = np.zeros(2, dtype=mapc.POSVELO_DTYPE)
+    p["pos"][1, 0] = 12.0
+    got = gpu_steps(mapc, p, 1)
+    a = 70000.0 * 12.0 / 2197.0
+    np.testing.assert_allclose(got["pos"][:, 3], [a, a], rtol=1e-6)
+    np.testing.assert_allclose(got["velo"][:, 0], [a * 0.1, -a * 0.1], rtol=1e-6)
+    q = np.zeros(3, dtype=mapc.POSVELO_DTYPE)
+    q["pos"][:, :3] = 5.0
+    got = gpu_steps(mapc, q, 1)
+    assert np.all(got["pos"][:, 3] == 0.0) and np.all(got["velo"] == 0.0)
+    assert np.all(got["pos"][:, :3] == 5.0)
+
+
+def test_n_active_and_ping_pong(mapc, oracle, gpu):
+    """KAT 8: step k reads side 1-b, writes side b, flips; bodies past the dispatch stay stale."""
+    n, active = 1000, 100
+    p = gentle_sphere(mapc, n, seed=5, speed=3.0)
+    sides = [p.copy(), p.copy()]            # both sides initialised alike (Compute.cpp:881-904)
+    b = 0
+    with mapc.Compute(n, 0) as c:
+        c.Upload(p)
+        assert c.GetSharedHandles().m_bufferIndex == 0
+        for k in range(3):
+            c.Simulate(active, 0)
+            oracle.step_allpairs(sides[1 - b], n_active=active, out=sides[b])
+            b = 1 - b
+            assert c.GetSharedHandles().m_bufferIndex == b
+            c.WaitForGpu()
+            got = c.Download()
+            ref = sides[1 - b]
+            assert_close(oracle, got[:128], ref[:128], TOL_10, f"step {k}")
+            assert got[128:].tobytes() == p[128:].tobytes()    # never dispatched: still the upload
+
+
+def test_fence_values(mapc, gpu):
+    p = gentle_sphere(mapc, 256, seed=1)
+    with mapc.Compute(256, 0) as c:
+        v0 = c.GetFenceValue()
+        assert v0 >= 2          # 0 -> 1 at creation (Compute.cpp:436), +1 for the ctor's WaitForGpu (:97)
+        c.Upload(p)
+        v1 = c.GetFenceValue()
+        assert v1 == v0 + 1     # InitializeParticles ends with WaitForGpu (Compute.cpp:922)
+        sh = c.GetSharedHandles()
+        for k in range(5):
+            f = c.GetFenceValue()
+            assert f == v1 + k  # the value the upcoming Simulate signals (Compute.h:64)
+            c.Simulate(256, 0)
+            sh.m_fence.Wait(f)
+            assert sh.m_fence.GetCompletedValue() >= f
+        c.WaitForGpu()
+        assert c.GetFenceValue() == v1 + 6
+
+
+def test_consumer_fence_gates_the_producer(mapc, gpu):
+    """Simulate(F) must not run before the consumer fence reaches F-1 (Compute.cpp:1012)."""
+    p = gentle_sphere(mapc, 512, seed=2)
+    consumer = mapc.Fence(0)
+    with mapc.Compute(512, 0) as c:
+        c.Upload(p)
+        sh = c.GetSharedHandles(consumer)
+        f = c.GetFenceValue()
+        try:
+            c.Simulate(512, 5)              # waits for consumer >= 4
+            time.sleep(0.2)
+            assert sh.m_fence.GetCompletedValue() < f, "producer ran ahead of the consumer fence"
+        finally:
+            consumer.Signal(4)              # never leave the stream blocked
+        sh.m_fence.Wait(f, timeout_ms=20000)
+        c.WaitForGpu()
+        c.GetSharedHandles(None)            # detach before the fence dies
+    consumer.close()
+
+
+def test_copy_state_and_migration_ctor(mapc, oracle, gpu):
+    n = 2048
+    p = gentle_sphere(mapc, n, seed=8, speed=2.0)
+    with mapc.Compute(n, 0) as a:
+        a.Upload(p)
+        for _ in range(3):
+            a.Simulate(n, 0)
+        with mapc.Compute(n, 0, a) as b:        # Compute(n, adapter, ext, prev) -> CopyState
+            assert b.Download().tobytes() == a.Download().tobytes()
+            a.Simulate(n, 0)
+            b.Simulate(n, 0)
+            a.WaitForGpu(); b.WaitForGpu()
+            assert b.Download().tobytes() == a.Download().tobytes()
+        with mapc.Compute(n, 0) as d:
+            d.CopyState(a)
+            assert d.Download().tobytes() == a.Download().tobytes()
+            with pytest.raises(mapc.MapcError):
+                with mapc.Compute(n // 2, 0) as e:
+                    e.CopyState(a)
+
+
+def test_launch_geometry_does_not_change_bits(mapc, gpu):
+    """P (pairs/thread) and T (block size) only regroup targets: results must be bit-identical."""
+    n = 5000
+    p = gentle_sphere(mapc, n, seed=13, speed=1.0)
+    base = gpu_steps(mapc, p, 2)
+    try:
+        for pairs, threads in ((4, 256), (4, 128), (2, 128), (1, 128), (1, 64)):
+            os.environ["MAPC_PLAN_PAIRS"], os.environ["MAPC_PLAN_THREADS"] = str(pairs), str(threads)
+            with mapc.Compute(n, 0) as c:
+                plan = c.Plan()
+                assert (plan["pairs_per_thread"], plan["threads_per_block"]) == (pairs, threads)
+            assert gpu_steps(mapc, p, 2).tobytes() == base.tobytes(), (pairs, threads)
+    finally:
+        os.environ.pop("MAPC_PLAN_PAIRS", None)
+        os.environ.pop("MAPC_PLAN_THREADS", None)
+
+
+def test_errors_are_loud(mapc, gpu):
+    with mapc.Compute(128, 0) as c:
+        with pytest.raises(mapc.MapcError):
+            c.Simulate(128, 0)                  # no particle state yet
+        c.Upload(gentle_sphere(mapc, 128, seed=1))
+        with pytest.raises(mapc.MapcError):
+            c.Simulate(129, 0)
+        with pytest.raises(mapc.MapcError):
+            c.Download(100, 100)
+        with pytest.raises(mapc.MapcError):
+            c.Upload(gentle_sphere(mapc, 64, seed=1))
+        with pytest.raises(mapc.MapcError):
+            c.SetForceMode(7)
+    with pytest.raises(mapc.MapcError):
+        mapc.Compute(128, 99)
+
+
+def test_gpu_timer_and_launch_counter(mapc, gpu):
+    n = 4096
+    with mapc.Compute(n, 0) as c:
+        c.Upload(gentle_sphere(mapc, n, seed=3))
+        before = c.KernelLaunches()
+        for _ in range(8):
+            c.Simulate(n, 0)
+        c.WaitForGpu()
+        assert c.KernelLaunches() == before + 16      # force + integrate per step
+        times, last_ms = c.GetGpuTimes()
+        assert times[0][1] == "simulate ms" and times[0][0] > 0 and last_ms > 0
+
+
+def test_init_particles_two_shells(mapc, gpu):
+    n = 4096
+    with mapc.Compute(n, 0) as c:
+        c.InitializeParticles(seed=42)
+        p = c.Download()
+    half = n // 2
+    for sl, cx in ((slice(0, half), 300.0), (slice(half, n), -300.0)):
+        d = p["pos"][sl, :3] - np.array([cx, 0, 0], dtype=np.float32)
+        np.testing.assert_allclose(np.linalg.norm(d, axis=1), 400.0, rtol=1e-5)
+    speed = np.linalg.norm(p["velo"][:, :3], axis=1)
+    assert speed.max() <= 15.0 * (1 + 1e-5) and speed.mean() > 5.0
+    # velocity is tangential: perpendicular to the direction to the origin
+    dots = np.einsum("ij,ij->i", p["velo"][:, :3], p["pos"][:, :3])
+    assert np.abs(dots).max() < 1e-2 * 15.0 * 700.0
+
+
+def test_full_size_262144_properties_and_subsampled_parity(mapc, oracle, gpu):
+    """BASELINE config 3 at full size: subsampled oracle parity + momentum + determinism."""
+    p = mapc.ic.workload("sphere_262144")
+    n = p.shape[0]
+    got = gpu_steps(mapc, p, 1)
+    rng = np.random.default_rng(0)
+    idx = np.sort(rng.choice(n, 2048, replace=False)).astype(np.int32)
+    ref = oracle.step_allpairs_targets(p, idx)
+    err = oracle.rel_errors(got[idx], ref)
+    assert max(err.values()) <= TOL_1, err
+    # antisymmetry: sum of accelerations (= velocities/dt, v0 = 0) cancels
+    v = got["velo"][:, :3].astype(np.float64)
+    assert np.all(np.abs(v.sum(axis=0)) < 1e-5 * np.abs(v).sum(axis=0))
+    # determinism: a second run is bit-identical
+    assert gpu_steps(mapc, p, 1).tobytes() == got.tobytes()
