@@ -245,13 +245,15 @@ void resolve_timers(mapc_compute *c, bool block)
     }
 }
 
-template <int P, int T>
+// Launch shapes measured on B200 at N = 262,144 (tools/ubench, profiles/r01_ubench_shapes.txt):
+// all sit on the same 70-72 % plateau, so the choice is about wave quantisation, not the inner loop.
+template <int P, int T, int U, int MINB, int ORDER>
 mapc_status launch_force(mapc_compute *c, const float4 *pos, int n_targets, int n_sources, int S,
                          const mapc::SegList &segs, int blocks_x)
 {
     if (segs.count == 0 || n_targets <= 0) return MAPC_OK;
     dim3 grid((unsigned)blocks_x, (unsigned)segs.count, 1);
-    mapc::force_segments_kernel<P, T><<<grid, T, 0, c->compute>>>(
+    mapc::force_segments_kernel<P, T, U, MINB, ORDER><<<grid, T, 0, c->compute>>>(
         pos, c->partial, (int)c->i_first, n_targets, n_sources, S, segs, (int)c->n_local);
     MAPC_CUDA(cudaGetLastError());
     ++c->launches;
@@ -263,14 +265,14 @@ mapc_status launch_force_plan(mapc_compute *c, const Plan &pl, const float4 *pos
 {
     const int S = pl.segments;
     if (pl.pairs == 4 && pl.threads == 256)
-        return launch_force<4, 256>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
+        return launch_force<4, 256, 8, 2, 0>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
     if (pl.pairs == 4 && pl.threads == 128)
-        return launch_force<4, 128>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
+        return launch_force<4, 128, 8, 4, 0>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
     if (pl.pairs == 2 && pl.threads == 128)
-        return launch_force<2, 128>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
+        return launch_force<2, 128, 4, 4, 2>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
     if (pl.pairs == 1 && pl.threads == 128)
-        return launch_force<1, 128>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
-    return launch_force<1, 64>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
+        return launch_force<1, 128, 8, 8, 0>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
+    return launch_force<1, 64, 8, 8, 0>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
 }
 
 // targets of this shard that a Simulate(n_active) updates, as a count from i_first

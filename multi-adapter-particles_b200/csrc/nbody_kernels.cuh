@@ -61,6 +61,13 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 //   invDistCube = (inv*inv)*inv      (:52)   2 FMUL2
 //   s = mass * invDistCube [* 1]     (:54)   FMUL2 (particles == 1 is an exact no-op)
 //   ai += r * s                      (:56)   3 FFMA2
+//
+// SCALAR_ACC: the three accumulations read three distinct register pairs each (r, s, ai).  The
+// register file feeds a packed FFMA2 only two fresh pairs per issue (measured: 3 cycles instead of
+// 2 when all three differ, tools/ubench), while scalar FFMA runs 3-operand at full rate -- so the
+// accumulations are issued as six scalar FFMAs on the halves of the same registers.  Same IEEE
+// fma per lane either way: the bits do not change.
+template <bool SCALAR_ACC>
 __device__ __forceinline__ void pair_interaction(const float4 b, const float2 nxi, const float2 nyi,
                                                  const float2 nzi, float2 &ax, float2 &ay, float2 &az)
 {
@@ -76,17 +83,70 @@ __device__ __forceinline__ void pair_interaction(const float4 b, const float2 nx
     const float2 inv2 = __fmul2_rn(inv, inv);
     const float2 inv3 = __fmul2_rn(inv2, inv);
     const float2 s = __fmul2_rn(inv3, make_float2(MAPC_PARTICLE_MASS, MAPC_PARTICLE_MASS));
-    ax = __ffma2_rn(dx, s, ax);
-    ay = __ffma2_rn(dy, s, ay);
-    az = __ffma2_rn(dz, s, az);
+    if (SCALAR_ACC) {
+        ax.x = __fmaf_rn(dx.x, s.x, ax.x);
+        ax.y = __fmaf_rn(dx.y, s.y, ax.y);
+        ay.x = __fmaf_rn(dy.x, s.x, ay.x);
+        ay.y = __fmaf_rn(dy.y, s.y, ay.y);
+        az.x = __fmaf_rn(dz.x, s.x, az.x);
+        az.y = __fmaf_rn(dz.y, s.y, az.y);
+    } else {
+        ax = __ffma2_rn(dx, s, ax);
+        ay = __ffma2_rn(dy, s, ay);
+        az = __ffma2_rn(dz, s, az);
+    }
+}
+
+// The same arithmetic for all P pairs of a thread against one source body, written operation-major
+// (every step looped over the pairs) so neighbouring instructions share operands: the broadcast
+// source coordinate across the subtractions and the scale s across the three accumulations, which is
+// what lets the register-reuse cache feed the 3-operand FFMA2s.  Rounding is untouched.
+template <int P>
+__device__ __forceinline__ void group_interaction(const float4 b, const float2 *nxi, const float2 *nyi,
+                                                  const float2 *nzi, float2 *ax, float2 *ay, float2 *az)
+{
+    float2 dx[P], dy[P], dz[P], d2[P], s[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) dx[p] = __fadd2_rn(make_float2(b.x, b.x), nxi[p]);
+#pragma unroll
+    for (int p = 0; p < P; ++p) dy[p] = __fadd2_rn(make_float2(b.y, b.y), nyi[p]);
+#pragma unroll
+    for (int p = 0; p < P; ++p) dz[p] = __fadd2_rn(make_float2(b.z, b.z), nzi[p]);
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+        d2[p] = __ffma2_rn(dx[p], dx[p], make_float2(MAPC_SOFTENING_SQUARED, MAPC_SOFTENING_SQUARED));
+#pragma unroll
+    for (int p = 0; p < P; ++p) d2[p] = __ffma2_rn(dy[p], dy[p], d2[p]);
+#pragma unroll
+    for (int p = 0; p < P; ++p) d2[p] = __ffma2_rn(dz[p], dz[p], d2[p]);
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        d2[p].x = rsqrt_approx(d2[p].x);
+        d2[p].y = rsqrt_approx(d2[p].y);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) s[p] = __fmul2_rn(d2[p], d2[p]);
+#pragma unroll
+    for (int p = 0; p < P; ++p) s[p] = __fmul2_rn(s[p], d2[p]);
+#pragma unroll
+    for (int p = 0; p < P; ++p) s[p] = __fmul2_rn(s[p], make_float2(MAPC_PARTICLE_MASS, MAPC_PARTICLE_MASS));
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        ax[p] = __ffma2_rn(dx[p], s[p], ax[p]);
+        ay[p] = __ffma2_rn(dy[p], s[p], ay[p]);
+        az[p] = __ffma2_rn(dz[p], s[p], az[p]);
+    }
 }
 
 // One block = T threads x 2P targets against one canonical segment of sources.
 //   pos            packed float4 positions, global indexing (targets and sources)
 //   partial        [S][partial_stride] float4, local target indexing
 //   i_first/i_cnt  local targets are bodies [i_first, i_first + i_cnt)
-template <int P, int T>
-__global__ void __launch_bounds__(T)
+// U = unroll of the source loop, MINB = resident blocks per SM asked of ptxas (register cap).
+// Neither P, T, U nor MINB changes any rounding: each target's chain is the same ops in the
+// same ascending-j order.
+template <int P, int T, int U, int MINB, int ORDER = 0>
+__global__ void __launch_bounds__(T, MINB)
 force_segments_kernel(const float4 *__restrict__ pos, float4 *__restrict__ partial, int i_first,
                       int i_cnt, int n_sources, int S, SegList segs, int partial_stride)
 {
@@ -146,21 +206,30 @@ force_segments_kernel(const float4 *__restrict__ pos, float4 *__restrict__ parti
         }
         const int cnt = (j1 - jt) < kTileBodies ? (j1 - jt) : kTileBodies;
         if (cnt == kTileBodies) {
-#pragma unroll 8
+            constexpr int kU = U;
+#pragma unroll kU
             for (int j = 0; j < kTileBodies; ++j) {
                 const float4 b = tile[buf][j];
+                if (ORDER == 2) {
+                    group_interaction<P>(b, nxi, nyi, nzi, ax, ay, az);
+                } else {
 #pragma unroll
-                for (int p = 0; p < P; ++p)
-                    pair_interaction(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+                    for (int p = 0; p < P; ++p)
+                        pair_interaction<ORDER == 1>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+                }
             }
         } else {
             // ragged last tile of the segment: loop bounded at the real count, no phantom bodies
-#pragma unroll 2
+#pragma unroll 1
             for (int j = 0; j < cnt; ++j) {
                 const float4 b = tile[buf][j];
+                if (ORDER == 2) {
+                    group_interaction<P>(b, nxi, nyi, nzi, ax, ay, az);
+                } else {
 #pragma unroll
-                for (int p = 0; p < P; ++p)
-                    pair_interaction(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+                    for (int p = 0; p < P; ++p)
+                        pair_interaction<ORDER == 1>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+                }
             }
         }
         if (has_next) {

@@ -79,6 +79,29 @@ def plummer(n: int, scale_radius: float, seed: int, truncate: float = 10.0,
     return _pack(pos, vel)
 
 
+def lattice_sphere(n: int, radius: float, seed: int, jitter: float = 0.25, speed: float = 0.0) -> np.ndarray:
+    """``n`` bodies on a jittered cubic lattice clipped to a sphere, in seeded random order.
+
+    Every pair is at least (1 - 2*jitter) lattice spacings apart, so there are no close
+    encounters at the softening scale: multi-step runs stay well conditioned and a parity
+    tolerance measures arithmetic, not chaotic amplification of the last bit."""
+    spacing = radius * (4.0 / 3.0 * np.pi / (1.3 * n)) ** (1.0 / 3.0)
+    while True:
+        m = int(np.ceil(radius / spacing)) + 1
+        g = np.arange(-m, m + 1, dtype=np.float64) * spacing
+        x, y, z = np.meshgrid(g, g, g, indexing="ij")
+        pts = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)
+        pts = pts[(pts * pts).sum(axis=1) <= radius * radius]
+        if pts.shape[0] >= n:
+            break
+        spacing *= 0.97
+    u = uniforms(seed, pts.shape[0], 6)
+    order = np.argsort(u[0], kind="stable")[:n]
+    pts = pts[order] + (u[1:4, order].T - 0.5) * (2.0 * jitter * spacing)
+    vel = _directions(u[4, order], u[5, order]) * speed
+    return _pack(pts, vel)
+
+
 #: the BASELINE.json / SURVEY.md section 8(d) workloads: name -> (N, generator)
 def workload(name: str) -> np.ndarray:
     if name == "interactive_10k":      # config 2: N=10,000 uniform sphere R=2000 seed 1
