@@ -39,15 +39,14 @@ SEED = 2
 DT, DAMPING = 0.1, 1.0               # Particles/Compute.cpp:545-546
 
 
-def workload_n(world: int, scaling: str, n_override: int | None) -> int:
-    """Weak scaling keeps the per-GPU work (N^2 / world pairs) fixed: N = 262,144 * sqrt(world),
-    rounded to a multiple of 64 * 8 * world so shards and canonical segments stay tile aligned."""
+def workload_n(pkg, world: int, scaling: str, n_override: int | None) -> int:
+    """Weak scaling (default) keeps the per-GPU work fixed: N = 262,144 * sqrt(world) (dist.weak_scaled_n);
+    --scaling strong runs BASELINE config 5's N = 4,194,304 at every GPU count."""
     if n_override:
         return n_override
-    if world == 1 or scaling == "strong":
-        return BASE_N if scaling != "strong" or world == 1 else 4_194_304
-    q = 64 * 8 * world
-    return int(round(BASE_N * math.sqrt(world) / q)) * q
+    if scaling == "strong":
+        return 4_194_304
+    return pkg.dist.weak_scaled_n(world, BASE_N)
 
 
 def make_particles(pkg, n: int) -> np.ndarray:
@@ -156,7 +155,7 @@ def run_reference(args) -> None:
     orc = importlib.import_module("oracle.oracle_py")
     orc.load()
     world = args.gpus
-    n = workload_n(world, args.scaling, args.n)
+    n = workload_n(pkg, world, args.scaling, args.n)
     particles = make_particles(pkg, n)
     threads = orc.max_threads()
     budget = max(2.0, min(20.0, 150.0 / (args.steps + args.warmup)))
@@ -197,22 +196,15 @@ def run_mapc(args) -> None:
         torch.cuda.synchronize()
 
     def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return pkg.dist.max_over_ranks(x, dev)
 
-    n = workload_n(world, args.scaling, args.n)
+    n = workload_n(pkg, world, args.scaling, args.n)
     particles = make_particles(pkg, n)
 
     nccl_id = None
     if world > 1:
-        buf = torch.zeros(pkg.NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(buf, 0)
-        nccl_id = bytes(buf.cpu().numpy().tobytes())
+        nccl_id = pkg.dist.broadcast_bytes(pkg.nccl_unique_id() if rank == 0 else None,
+                                           pkg.NCCL_UNIQUE_ID_BYTES, 0, dev)
 
     c = pkg.Compute(n, local_rank, rank=rank, world=world, nccl_id=nccl_id)
     c.Upload(particles)

@@ -192,6 +192,38 @@ MAPC_API mapc_status mapc_compute_copy_state(mapc_compute *dst, mapc_compute *sr
  * seed is an argument so runs are reproducible. */
 MAPC_API mapc_status mapc_compute_init_particles(mapc_compute *c, uint32_t seed);
 
+/* ---- headless consumer ------------------------------------------------------------------------
+ * Takes the place of the Render worker as the consumer of simulation results, keeping its fence
+ * protocol and one-frame latency (Particles/Render.cpp:789-831 CopySimulationResults, :839-937
+ * Draw, :653-677 MoveToNextFrame): a COPY stream pulls the packed positions of the side the
+ * previous Simulate wrote into a buffer local to the consumer's device (peer copy across devices,
+ * the cross-adapter heap's job in the reference), and a "render" stream consumes the local buffer
+ * -- headless, that is a dump to pinned host memory instead of DrawInstanced + Present.
+ * Fences: copy fence (shared with the producer, Render.cpp:605-618), render fence (frame throttle).
+ * Frame loop, exactly Particles::Draw (Particles.cpp:446-456):
+ *     F = mapc_compute_fence_value(compute);
+ *     mapc_consumer_draw(consumer, nDraw, &F, nCopy);
+ *     mapc_compute_simulate(compute, nSim, dt, damping, F);
+ */
+typedef struct mapc_consumer mapc_consumer;
+/* Render::Render + Particles::ShareHandles (Particles.cpp:191-208): attaches the consumer's copy
+ * fence to `producer` (GetSharedHandles), adopts its buffer index (SetShared, Render.cpp:222-224)
+ * and copies the initial positions into both local buffers. */
+MAPC_API mapc_status mapc_consumer_create(mapc_consumer **out, mapc_compute *producer, int device);
+MAPC_API mapc_status mapc_consumer_destroy(mapc_consumer *r);
+/* HANDLE Render::Draw(int numActive, Particles*, UINT64& inout_fenceValue, int numCopied),
+ * Render.cpp:839-938, non-async path.  in: the fence value the upcoming Simulate will signal;
+ * out: the consumer fence value that Simulate must pass on.  Blocks the host only when two frames
+ * are already in flight (the returned-handle wait of Particles.cpp:452-456). */
+MAPC_API mapc_status mapc_consumer_draw(mapc_consumer *r, int num_active_particles,
+                                        uint64_t *inout_fence_value, int num_particles_copied);
+/* Positions (x, y, z, |accel|) of the newest completed frame in pinned host memory, the frame
+ * number (0 = initial state) and how many bodies it holds.  Valid until the next draw call. */
+MAPC_API mapc_status mapc_consumer_latest(mapc_consumer *r, const float **host_positions,
+                                          uint64_t *frame, uint32_t *count);
+/* Render::WaitForGpu, Render.cpp:626-647: drains copy and render streams */
+MAPC_API mapc_status mapc_consumer_wait_for_gpu(mapc_consumer *r);
+
 /* ---- plan / diagnostics -------------------------------------------------------------------- */
 /* canonical number of j segments for n sources: 8 when n >= 131072 else 32.  The partial sums
  * of the segments are combined left to right, independent of the GPU count. */

@@ -23,7 +23,7 @@ from ctypes import (POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32
 
 import numpy as np
 
-from . import ic  # noqa: F401  (re-exported)
+from . import dist, ic  # noqa: F401  (re-exported)
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
@@ -64,6 +64,8 @@ EXPORTED_SYMBOLS = (
     "mapc_compute_copy_state", "mapc_compute_init_particles", "mapc_plan_segments",
     "mapc_compute_kernel_launches", "mapc_compute_plan", "mapc_fp32_peak_probe",
     "mapc_compute_step_times", "mapc_compute_flush",
+    "mapc_consumer_create", "mapc_consumer_destroy", "mapc_consumer_draw", "mapc_consumer_latest",
+    "mapc_consumer_wait_for_gpu",
 )
 
 
@@ -147,6 +149,11 @@ def load() -> ctypes.CDLL:
         "mapc_fp32_peak_probe": (c_int, [c_int, c_int, P(c_float), P(c_float)]),
         "mapc_compute_step_times": (c_int, [c_void_p, P(c_float), c_int, P(c_int)]),
         "mapc_compute_flush": (c_int, [c_void_p]),
+        "mapc_consumer_create": (c_int, [P(c_void_p), c_void_p, c_int]),
+        "mapc_consumer_destroy": (c_int, [c_void_p]),
+        "mapc_consumer_draw": (c_int, [c_void_p, c_int, P(c_uint64), c_int]),
+        "mapc_consumer_latest": (c_int, [c_void_p, P(P(c_float)), P(c_uint64), P(c_uint32)]),
+        "mapc_consumer_wait_for_gpu": (c_int, [c_void_p]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -350,6 +357,52 @@ class Compute:
     def close(self) -> None:
         if self._h:
             self._lib.mapc_compute_destroy(self._h)
+            self._h = c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Consumer:
+    """Headless stand-in for the reference's ``Render`` worker (Particles/Render.cpp:789-937): a
+    copy stream pulls each step's positions to its own device and dumps them to pinned host memory,
+    with the reference's copy-fence / render-fence protocol and one-frame latency."""
+
+    def __init__(self, compute: Compute, device: int = 0):
+        self._lib = load()
+        self._h = c_void_p()
+        self._compute = compute
+        _check(self._lib.mapc_consumer_create(byref(self._h), compute._h, device))
+
+    def Draw(self, in_numActiveParticles: int, inout_fenceValue: int, in_numParticlesCopied: int | None = None) -> int:
+        """``Render::Draw``; returns the fence value to hand to ``Compute.Simulate``."""
+        f = c_uint64(inout_fenceValue)
+        n_copy = in_numActiveParticles if in_numParticlesCopied is None else in_numParticlesCopied
+        _check(self._lib.mapc_consumer_draw(self._h, in_numActiveParticles, byref(f), n_copy))
+        return int(f.value)
+
+    def Latest(self):
+        """(frame number, float32[count, 4] copy of the newest completed position dump)."""
+        ptr, frame, count = POINTER(c_float)(), c_uint64(0), c_uint32(0)
+        _check(self._lib.mapc_consumer_latest(self._h, byref(ptr), byref(frame), byref(count)))
+        arr = np.ctypeslib.as_array(ptr, shape=(count.value, 4)).copy() if count.value else np.zeros((0, 4), np.float32)
+        return int(frame.value), arr
+
+    def WaitForGpu(self) -> None:
+        _check(self._lib.mapc_consumer_wait_for_gpu(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.mapc_consumer_destroy(self._h)
             self._h = c_void_p()
 
     def __enter__(self):

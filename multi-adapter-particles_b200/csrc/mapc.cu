@@ -813,6 +813,191 @@ mapc_status mapc_fp32_peak_probe(int device, int packed, float *tflops, float *m
     return MAPC_OK;
 }
 
+// ---- headless consumer (the Render worker's role) ----------------------------------------------
+}  // extern "C"
+
+struct mapc_consumer {
+    mapc_compute *producer = nullptr;
+    int device = 0;
+    uint32_t n = 0;
+    cudaStream_t copy = nullptr;     // m_copyQueue
+    cudaStream_t render = nullptr;   // m_commandQueue (direct queue): consumes the local buffer
+    float4 *local[2] = {nullptr, nullptr};   // m_buffers: positions local to the consumer's device
+    float4 *host[2] = {nullptr, nullptr};    // pinned dump targets ("the screen")
+    mapc_fence *copy_fence = nullptr;        // m_copyFence, shared with the producer
+    mapc_fence *render_fence = nullptr;      // m_renderFence
+    mapc_fence *compute_fence = nullptr;     // m_sharedComputeFence (borrowed)
+    uint64_t copy_fence_value = 0, render_fence_value = 0;
+    uint64_t frame_fence_values[2] = {0, 0};
+    uint32_t shared_buffer_index = 0;        // m_sharedBufferIndex
+    uint32_t current_buffer_index = 0;       // m_currentBufferIndex
+    uint32_t frame_index = 0;                // m_frameIndex (two frames in flight)
+    uint64_t frames_drawn = 0;
+    uint64_t host_frame[2] = {0, 0};         // simulation step held by host[i]
+    uint64_t host_fence[2] = {0, 0};         // render fence value that marks host[i] complete
+    uint32_t host_count[2] = {0, 0};
+    uint64_t local_frame[2] = {0, 0};        // simulation step held by local[i]
+    uint64_t copies = 0;
+};
+
+extern "C" {
+
+mapc_status mapc_consumer_destroy(mapc_consumer *r)
+{
+    if (!r) return MAPC_OK;
+    DeviceGuard g(r->device);
+    if (r->copy) cudaStreamSynchronize(r->copy);
+    if (r->render) cudaStreamSynchronize(r->render);
+    if (r->producer && r->producer->consumer_fence == r->copy_fence) r->producer->consumer_fence = nullptr;
+    for (int i = 0; i < 2; ++i) {
+        if (r->local[i]) cudaFree(r->local[i]);
+        if (r->host[i]) cudaFreeHost(r->host[i]);
+    }
+    if (r->copy) cudaStreamDestroy(r->copy);
+    if (r->render) cudaStreamDestroy(r->render);
+    mapc_fence_destroy(r->copy_fence);
+    mapc_fence_destroy(r->render_fence);
+    delete r;
+    return MAPC_OK;
+}
+
+mapc_status mapc_consumer_wait_for_gpu(mapc_consumer *r)
+{
+    if (!r) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL consumer");
+    DeviceGuard g(r->device);
+    // Render::WaitForGpu, Render.cpp:626-647: copy fence, then render fence, then host wait
+    r->copy_fence_value++;
+    MAPC_TRY(mapc_fence_signal_stream(r->copy_fence, r->copy, r->copy_fence_value));
+    MAPC_TRY(mapc_fence_wait_stream(r->copy_fence, r->render, r->copy_fence_value));
+    MAPC_TRY(mapc_fence_signal_stream(r->render_fence, r->render, r->render_fence_value));
+    r->render_fence_value++;
+    MAPC_CUDA(cudaStreamSynchronize(r->copy));
+    MAPC_CUDA(cudaStreamSynchronize(r->render));
+    return MAPC_OK;
+}
+
+mapc_status mapc_consumer_create(mapc_consumer **out, mapc_compute *producer, int device)
+{
+    if (!out || !producer) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    if (producer->world != 1)
+        return fail(MAPC_ERR_UNSUPPORTED, "the headless consumer attaches to an unsharded Compute");
+    if (!producer->has_state) return fail(MAPC_ERR_INVALID_ARGUMENT, "producer has no particle state");
+    int count = 0;
+    MAPC_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(MAPC_ERR_INVALID_ARGUMENT, "device %d out of range", device);
+    MAPC_TRY(mapc_compute_wait_for_gpu(producer));
+    DeviceGuard g(device);
+    mapc_consumer *r = new (std::nothrow) mapc_consumer();
+    if (!r) return fail(MAPC_ERR_OUT_OF_MEMORY, "host allocation failed");
+    r->producer = producer;
+    r->device = device;
+    r->n = producer->n;
+    auto body = [&]() -> mapc_status {
+        MAPC_CUDA(cudaStreamCreateWithFlags(&r->copy, cudaStreamNonBlocking));
+        MAPC_CUDA(cudaStreamCreateWithFlags(&r->render, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            MAPC_CUDA(cudaMalloc(&r->local[i], (size_t)r->n * sizeof(float4)));
+            MAPC_CUDA(cudaHostAlloc(&r->host[i], (size_t)r->n * sizeof(float4), cudaHostAllocPortable));
+        }
+        MAPC_TRY(mapc_fence_create(&r->render_fence, 0));   // Render.cpp:588-595
+        r->render_fence_value = 1;
+        MAPC_TRY(mapc_fence_create(&r->copy_fence, 0));     // Render.cpp:611-617 (the shared one)
+        // Particles::ShareHandles, Particles.cpp:198-200
+        mapc_shared_handles sh;
+        MAPC_TRY(mapc_compute_shared_handles(producer, r->copy_fence, &sh));
+        r->shared_buffer_index = sh.buffer_index;           // Render.cpp:224
+        r->compute_fence = sh.fence;
+        // "copy initial state from the other adapter" (Render.cpp:253-): both local buffers
+        const uint32_t newest = 1u - sh.buffer_index;
+        for (int i = 0; i < 2; ++i)
+            MAPC_CUDA(cudaMemcpyPeerAsync(r->local[i], device, producer->packed[newest], producer->device,
+                                          (size_t)r->n * sizeof(float4), r->copy));
+        MAPC_CUDA(cudaMemcpyAsync(r->host[0], r->local[0], (size_t)r->n * sizeof(float4),
+                                  cudaMemcpyDeviceToHost, r->copy));
+        r->host_count[0] = r->n;
+        return mapc_consumer_wait_for_gpu(r);
+    };
+    const mapc_status st = body();
+    if (st != MAPC_OK) {
+        const std::string keep = g_last_error;
+        mapc_consumer_destroy(r);
+        g_last_error = keep;
+        return st;
+    }
+    *out = r;
+    return MAPC_OK;
+}
+
+mapc_status mapc_consumer_draw(mapc_consumer *r, int num_active_particles, uint64_t *inout_fence_value,
+                               int num_particles_copied)
+{
+    if (!r || !inout_fence_value) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (num_active_particles < 0 || (uint32_t)num_active_particles > r->n || num_particles_copied < 0 ||
+        (uint32_t)num_particles_copied > r->n)
+        return fail(MAPC_ERR_INVALID_ARGUMENT, "particle counts outside [0, %u]", r->n);
+    DeviceGuard g(r->device);
+    const uint64_t compute_fence_value = *inout_fence_value;
+
+    // ---- CopySimulationResults(in_fenceValue, in_numParticlesCopied), Render.cpp:789-831 ---------
+    // wait on the previous frame's render to finish with the local buffer (:796)
+    MAPC_TRY(mapc_fence_wait_stream(r->render_fence, r->copy, r->render_fence_value - 1));
+    const uint32_t src_shared = 1u - r->shared_buffer_index;   // :798
+    const uint32_t dst_local = 1u - r->current_buffer_index;   // :799
+    r->shared_buffer_index = 1u - r->shared_buffer_index;      // :800
+    if (num_particles_copied > 0)                              // :814 copy just the particles required
+        MAPC_CUDA(cudaMemcpyPeerAsync(r->local[dst_local], r->device, r->producer->packed[src_shared],
+                                      r->producer->device, (size_t)num_particles_copied * sizeof(float4),
+                                      r->copy));
+    r->local_frame[dst_local] = r->copies++;   // results of the PREVIOUS Simulate (step number = copies so far)
+    // don't start the next copy until the compute device has produced new results (:826)
+    MAPC_TRY(mapc_fence_wait_stream(r->compute_fence, r->copy, compute_fence_value));
+    r->copy_fence_value++;                                     // :829-830
+    MAPC_TRY(mapc_fence_signal_stream(r->copy_fence, r->copy, r->copy_fence_value));
+
+    // ---- the "draw" of local[m_currentBufferIndex] (:884-891): headless = dump to pinned host ------
+    const uint32_t cur = r->current_buffer_index;
+    r->current_buffer_index = 1u - r->current_buffer_index;    // :885
+    const uint32_t slot = r->frame_index;
+    if (num_active_particles > 0)
+        MAPC_CUDA(cudaMemcpyAsync(r->host[slot], r->local[cur], (size_t)num_active_particles * sizeof(float4),
+                                  cudaMemcpyDeviceToHost, r->render));
+    r->host_frame[slot] = r->local_frame[cur];
+    r->host_count[slot] = (uint32_t)num_active_particles;
+
+    // render waits for this frame's copy; hand the copy fence value to the producer (:925-926)
+    MAPC_TRY(mapc_fence_wait_stream(r->copy_fence, r->render, r->copy_fence_value));
+    *inout_fence_value = r->copy_fence_value;
+
+    // ---- MoveToNextFrame, Render.cpp:653-677 ---------------------------------------------------------
+    r->frame_fence_values[r->frame_index] = r->render_fence_value;
+    r->host_fence[slot] = r->render_fence_value;
+    MAPC_TRY(mapc_fence_signal_stream(r->render_fence, r->render, r->render_fence_value));
+    r->render_fence_value++;
+    r->frame_index = 1u - r->frame_index;                      // two "back buffers"
+    r->frames_drawn++;
+    // "If the next frame is not ready to be rendered yet, wait until it is ready" (:665-674; the
+    // reference returns the event and Particles::Draw waits on it, Particles.cpp:452-456)
+    if (mapc_fence_completed_value(r->render_fence) < r->frame_fence_values[r->frame_index])
+        MAPC_TRY(mapc_fence_wait_host(r->render_fence, r->frame_fence_values[r->frame_index], 60000));
+    return MAPC_OK;
+}
+
+mapc_status mapc_consumer_latest(mapc_consumer *r, const float **host_positions, uint64_t *frame, uint32_t *count)
+{
+    if (!r) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL consumer");
+    // newest slot whose render fence has been reached
+    int best = -1;
+    const uint64_t done = mapc_fence_completed_value(r->render_fence);
+    for (int i = 0; i < 2; ++i)
+        if (r->host_fence[i] <= done && (best < 0 || r->host_fence[i] > r->host_fence[best])) best = i;
+    if (best < 0) return fail(MAPC_ERR_INVALID_ARGUMENT, "no completed frame");
+    if (host_positions) *host_positions = reinterpret_cast<const float *>(r->host[best]);
+    if (frame) *frame = r->host_frame[best];
+    if (count) *count = r->host_count[best];
+    return MAPC_OK;
+}
+
 // ---- initial conditions (InitializeParticles / LoadParticles) -----------------------------------
 namespace {
 

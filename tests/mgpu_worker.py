@@ -1,0 +1,73 @@
+"""Multi-GPU parity worker, launched by tests/test_multi_gpu.py (or by hand) as
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node R --master-addr 127.0.0.1 \
+        --master-port P tests/mgpu_worker.py [--n N ...]
+
+Every rank drives one GPU through the C ABI (sharded handle, NCCL all-gather inside libmapc.so).
+After `steps` steps each rank compares its shard, BITWISE, with an unsharded run of the same
+problem on its own GPU: the canonical segment order must make results independent of the GPU count.
+"""
+import argparse
+import hashlib
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, nargs="+", default=[8192, 10_000, 32_768])
+    ap.add_argument("--steps", type=int, default=4)
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = (int(os.environ[k]) for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    pkg = importlib.import_module("multi-adapter-particles_b200")
+    pkg.load()
+    nccl_id = pkg.dist.broadcast_bytes(pkg.nccl_unique_id() if rank == 0 else None, pkg.NCCL_UNIQUE_ID_BYTES, 0, dev)
+
+    ok = True
+    for n in args.n:
+        if n % world:
+            continue
+        radius = 2000.0 * (n / 10_000.0) ** (1.0 / 3.0)
+        p = pkg.ic.uniform_sphere(n, radius, seed=n, speed=1.0)
+        with pkg.Compute(n, local_rank, rank=rank, world=world, nccl_id=nccl_id if n == args.n[0] else
+                         pkg.dist.broadcast_bytes(pkg.nccl_unique_id() if rank == 0 else None,
+                                                  pkg.NCCL_UNIQUE_ID_BYTES, 0, dev)) as c:
+            c.Upload(p)
+            for _ in range(args.steps):
+                c.Simulate(n, 0)
+            c.WaitForGpu()
+            mine = c.Download()
+            first, count = c.first_particle, c.num_local
+        with pkg.Compute(n, local_rank) as s:
+            s.Upload(p)
+            for _ in range(args.steps):
+                s.Simulate(n, 0)
+            s.WaitForGpu()
+            full = s.Download()
+        same = mine.tobytes() == full[first:first + count].tobytes()
+        digest = hashlib.sha256(full.tobytes()).hexdigest()[:16]
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"n={n} world={world} steps={args.steps} bit-identical={bool(flag.item())} sha256[:16]={digest}",
+                  flush=True)
+        ok = ok and bool(flag.item())
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -290,3 +290,35 @@ def test_full_size_262144_properties_and_subsampled_parity(mapc, oracle, gpu):
     assert np.all(np.abs(v.sum(axis=0)) < 1e-5 * np.abs(v).sum(axis=0))
     # determinism: a second run is bit-identical
     assert gpu_steps(mapc, p, 1).tobytes() == got.tobytes()
+
+
+def test_headless_consumer_frame_loop(mapc, oracle, gpu):
+    """Particles::Draw's loop (Particles.cpp:446-448) with the headless consumer: frame k dumps the
+    result of step k-1 (one-frame latency), the producer never overwrites a side the copy still
+    reads, and the dumped positions equal the oracle's trajectory."""
+    n = 2048
+    p = gentle_sphere(mapc, n, seed=4, speed=2.0)
+    states = [p]
+    for _ in range(6):
+        states.append(oracle.step_allpairs(states[-1], flavour=oracle.MIRRORED))
+    with mapc.Compute(n, 0) as c:
+        c.Upload(p)
+        with mapc.Consumer(c, 0) as r:
+            frame0, pos0 = r.Latest()
+            assert frame0 == 0 and pos0.tobytes() == p["pos"].tobytes()
+            seen = {}
+            for k in range(6):
+                fence = c.GetFenceValue()
+                fence = r.Draw(n, fence, n)
+                c.Simulate(n, fence)
+                r.WaitForGpu()
+                frame, pos = r.Latest()
+                seen[frame] = pos
+            c.WaitForGpu()
+            assert sorted(seen) == [0, 1, 2, 3, 4], sorted(seen)   # frame k shows step k-1
+            for frame, pos in seen.items():
+                ref = states[frame]["pos"]
+                scale = np.abs(ref[:, :3]).max()
+                assert np.abs(pos[:, :3] - ref[:, :3]).max() / scale <= TOL_10, frame
+            final = c.Download()
+            assert_close(oracle, final, states[6], TOL_10, "producer state after 6 frames")
