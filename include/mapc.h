@@ -221,6 +221,10 @@ MAPC_API mapc_status mapc_consumer_draw(mapc_consumer *r, int num_active_particl
  * number (0 = initial state) and how many bodies it holds.  Valid until the next draw call. */
 MAPC_API mapc_status mapc_consumer_latest(mapc_consumer *r, const float **host_positions,
                                           uint64_t *frame, uint32_t *count);
+/* Protocol counters for logs and tests: out[0] copy fence completed, out[1] copy fence value issued,
+ * out[2] render fence completed, out[3] render fence value to be issued next, out[4] shared buffer
+ * index, out[5] current (local) buffer index, out[6] frames drawn, out[7] copies issued. */
+MAPC_API mapc_status mapc_consumer_counters(const mapc_consumer *r, uint64_t out[8]);
 /* Render::WaitForGpu, Render.cpp:626-647: drains copy and render streams */
 MAPC_API mapc_status mapc_consumer_wait_for_gpu(mapc_consumer *r);
 

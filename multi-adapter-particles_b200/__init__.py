@@ -65,7 +65,7 @@ EXPORTED_SYMBOLS = (
     "mapc_compute_kernel_launches", "mapc_compute_plan", "mapc_fp32_peak_probe",
     "mapc_compute_step_times", "mapc_compute_flush",
     "mapc_consumer_create", "mapc_consumer_destroy", "mapc_consumer_draw", "mapc_consumer_latest",
-    "mapc_consumer_wait_for_gpu",
+    "mapc_consumer_wait_for_gpu", "mapc_consumer_counters",
 )
 
 
@@ -154,6 +154,7 @@ def load() -> ctypes.CDLL:
         "mapc_consumer_draw": (c_int, [c_void_p, c_int, P(c_uint64), c_int]),
         "mapc_consumer_latest": (c_int, [c_void_p, P(P(c_float)), P(c_uint64), P(c_uint32)]),
         "mapc_consumer_wait_for_gpu": (c_int, [c_void_p]),
+        "mapc_consumer_counters": (c_int, [c_void_p, P(c_uint64)]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -399,6 +400,13 @@ class Consumer:
 
     def WaitForGpu(self) -> None:
         _check(self._lib.mapc_consumer_wait_for_gpu(self._h))
+
+    def Counters(self) -> dict:
+        buf = (c_uint64 * 8)()
+        _check(self._lib.mapc_consumer_counters(self._h, buf))
+        names = ("copy_fence_completed", "copy_fence_value", "render_fence_completed", "render_fence_value",
+                 "shared_buffer_index", "current_buffer_index", "frames_drawn", "copies")
+        return dict(zip(names, (int(v) for v in buf)))
 
     def close(self) -> None:
         if self._h:

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "../../include/mapc.h"
+#include "fence.hpp"
 #include "nbody_kernels.cuh"
 
 namespace {
@@ -136,10 +137,141 @@ struct DeviceGuard {
 
 }  // namespace
 
-// ---- fence ----------------------------------------------------------------------------------
-struct mapc_fence {
-    volatile uint64_t *word = nullptr;  // pinned, portable, mapped; UVA: same address on devices
-};
+// ---- fences and gated streams (fence.hpp) -------------------------------------------------------
+namespace mapc {
+
+uint64_t fence_completed(const mapc_fence *f)
+{
+    return __atomic_load_n((const uint64_t *)f->word, __ATOMIC_ACQUIRE);
+}
+
+void fence_notify(mapc_fence *f)
+{
+    const std::vector<GatedStream *> waiters = f->waiters;  // draining may edit the list
+    for (GatedStream *gs : waiters) gs_drain(gs);
+}
+
+mapc_status fence_submit_signal(mapc_fence *f, cudaStream_t stream, int device, uint64_t value)
+{
+    MAPC_TRY(load_stream_memops());
+    DeviceGuard g(device);
+    // drop signals that have completed (their waits are no-ops from now on)
+    const uint64_t done = fence_completed(f);
+    while (f->signals.size() > 4 && f->signals.front().value <= done) {
+        cudaEventDestroy(f->signals.front().event);
+        f->signals.pop_front();
+    }
+    cudaEvent_t ev = nullptr;
+    MAPC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    MAPC_CUDA(cudaEventRecord(ev, stream));
+    const CUresult r = g_write64((CUstream)stream, (CUdeviceptr)(uintptr_t)f->word, value,
+                                 CU_STREAM_WRITE_VALUE_DEFAULT);
+    if (r != CUDA_SUCCESS) {
+        cudaEventDestroy(ev);
+        return fail(MAPC_ERR_CUDA, "cuStreamWriteValue64 failed: %d", (int)r);
+    }
+    f->signals.push_back(FenceSignal{value, ev});
+    if (value > f->submitted) f->submitted = value;
+    fence_notify(f);
+    return MAPC_OK;
+}
+
+mapc_status fence_submit_wait(mapc_fence *f, cudaStream_t stream, uint64_t value)
+{
+    if (fence_completed(f) >= value) return MAPC_OK;
+    for (const FenceSignal &sig : f->signals)
+        if (sig.value >= value) {
+            MAPC_CUDA(cudaStreamWaitEvent(stream, sig.event, 0));
+            return MAPC_OK;
+        }
+    // submitted >= value but no event: the value was signalled from the host and is visible already
+    return MAPC_OK;
+}
+
+static mapc_status run_op(GatedStream *gs, StreamOp &op)
+{
+    DeviceGuard g(gs->device);
+    switch (op.kind) {
+    case StreamOp::kWait: return fence_submit_wait(op.fence, gs->stream, op.value);
+    case StreamOp::kSignal: return fence_submit_signal(op.fence, gs->stream, gs->device, op.value);
+    default: return op.fn();
+    }
+}
+
+mapc_status gs_drain(GatedStream *gs)
+{
+    if (gs->draining) return MAPC_OK;  // an outer frame of this same drain continues the loop
+    gs->draining = true;
+    mapc_status st = MAPC_OK;
+    while (!gs->pending.empty()) {
+        StreamOp &op = gs->pending.front();
+        if (op.kind == StreamOp::kWait && !fence_ready(op.fence, op.value)) break;
+        StreamOp local = std::move(op);
+        gs->pending.pop_front();
+        if (local.kind == StreamOp::kWait) {
+            auto &w = local.fence->waiters;
+            bool still = false;
+            for (const StreamOp &o : gs->pending) still = still || (o.kind == StreamOp::kWait && o.fence == local.fence);
+            if (!still) w.erase(std::remove(w.begin(), w.end(), gs), w.end());
+        }
+        st = run_op(gs, local);
+        if (st != MAPC_OK) break;
+    }
+    gs->draining = false;
+    return st;
+}
+
+static mapc_status gs_push(GatedStream *gs, StreamOp op)
+{
+    if (gs->pending.empty() && !(op.kind == StreamOp::kWait && !fence_ready(op.fence, op.value)))
+        return run_op(gs, op);
+    if (op.kind == StreamOp::kWait) {
+        auto &w = op.fence->waiters;
+        if (std::find(w.begin(), w.end(), gs) == w.end()) w.push_back(gs);
+    }
+    gs->pending.push_back(std::move(op));
+    return gs_drain(gs);
+}
+
+mapc_status gs_wait(GatedStream *gs, mapc_fence *f, uint64_t value)
+{
+    return gs_push(gs, StreamOp{StreamOp::kWait, f, value, nullptr});
+}
+
+mapc_status gs_signal(GatedStream *gs, mapc_fence *f, uint64_t value)
+{
+    return gs_push(gs, StreamOp{StreamOp::kSignal, f, value, nullptr});
+}
+
+mapc_status gs_call(GatedStream *gs, std::function<mapc_status()> fn)
+{
+    return gs_push(gs, StreamOp{StreamOp::kCall, nullptr, 0, std::move(fn)});
+}
+
+void gs_detach(GatedStream *gs)
+{
+    for (StreamOp &op : gs->pending)
+        if (op.kind == StreamOp::kWait) {
+            auto &w = op.fence->waiters;
+            w.erase(std::remove(w.begin(), w.end(), gs), w.end());
+        }
+    gs->pending.clear();
+}
+
+// a stream that still has host-queued work is waiting for a signal nobody has submitted
+static mapc_status require_ungated(const GatedStream *gs, const char *what)
+{
+    if (gs->pending.empty()) return MAPC_OK;
+    for (const StreamOp &op : gs->pending)
+        if (op.kind == StreamOp::kWait)
+            return fail(MAPC_ERR_TIMEOUT,
+                        "%s: the stream is gated on fence value %llu whose signal has not been submitted "
+                        "(completed %llu) -- it would never finish",
+                        what, (unsigned long long)op.value, (unsigned long long)fence_completed(op.fence));
+    return fail(MAPC_ERR_TIMEOUT, "%s: stream has unsubmitted work", what);
+}
+
+}  // namespace mapc
 
 // ---- launch plan ------------------------------------------------------------------------------
 namespace {
@@ -192,6 +324,7 @@ struct mapc_compute {
     mapc_force_mode mode = MAPC_FORCE_ALLPAIRS;
 
     cudaStream_t compute = nullptr;  // m_commandQueue (compute)
+    mapc::GatedStream gcompute;      // the same stream behind the fence gate (fence.hpp)
     cudaStream_t comm = nullptr;     // all-gather stream
     mapc_posvelo *posvelo[2] = {nullptr, nullptr};  // ping-pong sides, local shard
     float4 *packed[2] = {nullptr, nullptr};         // packed positions, all N, per side
@@ -331,6 +464,8 @@ mapc_status create_common(mapc_compute **out, uint32_t n, int device, int rank, 
     auto body = [&]() -> mapc_status {
         MAPC_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
         MAPC_CUDA(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+        c->gcompute.stream = c->compute;
+        c->gcompute.device = device;
         MAPC_CUDA(cudaStreamCreateWithFlags(&c->comm, cudaStreamNonBlocking));
         for (int s = 0; s < 2; ++s) {
             MAPC_CUDA(cudaMalloc(&c->posvelo[s], (size_t)c->n_local * sizeof(mapc_posvelo)));
@@ -399,6 +534,7 @@ mapc_status mapc_fence_create(mapc_fence **out, uint64_t initial_value)
     }
     f->word = (volatile uint64_t *)p;
     *f->word = initial_value;
+    f->submitted = initial_value;
     *out = f;
     return MAPC_OK;
 }
@@ -406,20 +542,23 @@ mapc_status mapc_fence_create(mapc_fence **out, uint64_t initial_value)
 mapc_status mapc_fence_destroy(mapc_fence *f)
 {
     if (!f) return MAPC_OK;
+    // nothing may stay gated on a fence that is going away: treat its waits as satisfied
+    f->submitted = UINT64_MAX;
+    mapc::fence_notify(f);
+    for (mapc::FenceSignal &sig : f->signals) cudaEventDestroy(sig.event);
     if (f->word) cudaFreeHost((void *)f->word);
     delete f;
     return MAPC_OK;
 }
 
-uint64_t mapc_fence_completed_value(const mapc_fence *f)
-{
-    return f ? __atomic_load_n((const uint64_t *)f->word, __ATOMIC_ACQUIRE) : 0;
-}
+uint64_t mapc_fence_completed_value(const mapc_fence *f) { return f ? mapc::fence_completed(f) : 0; }
 
 mapc_status mapc_fence_signal_host(mapc_fence *f, uint64_t value)
 {
     if (!f) return fail(MAPC_ERR_INVALID_ARGUMENT, "fence is NULL");
     __atomic_store_n((uint64_t *)f->word, value, __ATOMIC_RELEASE);
+    if (value > f->submitted) f->submitted = value;
+    mapc::fence_notify(f);
     return MAPC_OK;
 }
 
@@ -434,32 +573,35 @@ mapc_status mapc_fence_wait_host(const mapc_fence *f, uint64_t value, int timeou
             const auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(
                                 std::chrono::steady_clock::now() - t0).count();
             if (ms > timeout_ms)
-                return fail(MAPC_ERR_TIMEOUT, "fence wait for %llu timed out at %llu",
-                            (unsigned long long)value,
-                            (unsigned long long)mapc_fence_completed_value(f));
+                return fail(MAPC_ERR_TIMEOUT, "fence wait for %llu timed out at %llu (submitted %llu)",
+                            (unsigned long long)value, (unsigned long long)mapc_fence_completed_value(f),
+                            (unsigned long long)f->submitted);
         }
     }
     return MAPC_OK;
 }
 
+// Raw-stream forms for callers that own their streams.  A raw stream cannot be gated, so waiting for a
+// value whose signal has not been submitted is refused instead of risking the hang described in fence.hpp.
 mapc_status mapc_fence_signal_stream(mapc_fence *f, void *cuda_stream, uint64_t value)
 {
     if (!f) return fail(MAPC_ERR_INVALID_ARGUMENT, "fence is NULL");
-    MAPC_TRY(load_stream_memops());
-    const CUresult r = g_write64((CUstream)cuda_stream, (CUdeviceptr)(uintptr_t)f->word, value,
-                                 CU_STREAM_WRITE_VALUE_DEFAULT);
-    if (r != CUDA_SUCCESS) return fail(MAPC_ERR_CUDA, "cuStreamWriteValue64 failed: %d", (int)r);
-    return MAPC_OK;
+    int device = 0;
+    MAPC_CUDA(cudaStreamGetDevice((cudaStream_t)cuda_stream, &device));
+    return mapc::fence_submit_signal(f, (cudaStream_t)cuda_stream, device, value);
 }
 
 mapc_status mapc_fence_wait_stream(const mapc_fence *f, void *cuda_stream, uint64_t value)
 {
     if (!f) return fail(MAPC_ERR_INVALID_ARGUMENT, "fence is NULL");
-    MAPC_TRY(load_stream_memops());
-    const CUresult r = g_wait64((CUstream)cuda_stream, (CUdeviceptr)(uintptr_t)f->word, value,
-                                CU_STREAM_WAIT_VALUE_GEQ);
-    if (r != CUDA_SUCCESS) return fail(MAPC_ERR_CUDA, "cuStreamWaitValue64 failed: %d", (int)r);
-    return MAPC_OK;
+    if (!mapc::fence_ready(f, value))
+        return fail(MAPC_ERR_UNSUPPORTED,
+                    "fence value %llu has not been signalled or submitted yet (submitted %llu): a raw stream "
+                    "cannot wait for future values", (unsigned long long)value, (unsigned long long)f->submitted);
+    int device = 0;
+    MAPC_CUDA(cudaStreamGetDevice((cudaStream_t)cuda_stream, &device));
+    DeviceGuard g(device);
+    return mapc::fence_submit_wait(const_cast<mapc_fence *>(f), (cudaStream_t)cuda_stream, value);
 }
 
 // ---- create / destroy ------------------------------------------------------------------------
@@ -502,6 +644,7 @@ mapc_status mapc_compute_destroy(mapc_compute *c)
     if (!c) return MAPC_OK;
     DeviceGuard g(c->device);
     // Compute::~Compute drains the queue first (Compute.cpp:104)
+    mapc::gs_detach(&c->gcompute);  // host-queued work gated on a signal that never came is dropped
     if (c->compute) cudaStreamSynchronize(c->compute);
     if (c->comm) cudaStreamSynchronize(c->comm);
     if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
@@ -528,6 +671,7 @@ mapc_status mapc_compute_upload(mapc_compute *c, const mapc_posvelo *host, uint3
 {
     if (!c || !host) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (n != c->n) return fail(MAPC_ERR_INVALID_ARGUMENT, "upload of %u bodies into a handle of %u", n, c->n);
+    MAPC_TRY(mapc::require_ungated(&c->gcompute, "Upload"));
     DeviceGuard g(c->device);
     // stage all N bodies once (side 1's packed array is big enough only for positions, so use a
     // temporary), then fan out: both PosVelo sides get the shard, both packed sides all N.
@@ -560,6 +704,7 @@ mapc_status mapc_compute_download(mapc_compute *c, mapc_posvelo *host, uint32_t 
     if (first < c->i_first || (uint64_t)first + count > (uint64_t)c->i_first + c->n_local)
         return fail(MAPC_ERR_INVALID_ARGUMENT, "range [%u, %u) outside shard [%u, %u)", first,
                     first + count, c->i_first, c->i_first + c->n_local);
+    MAPC_TRY(mapc::require_ungated(&c->gcompute, "Download"));
     DeviceGuard g(c->device);
     const uint32_t side = 1u - c->buffer_index;  // the side the last Simulate wrote
     MAPC_CUDA(cudaMemcpyAsync(host, c->posvelo[side] + (first - c->i_first),
@@ -586,32 +731,19 @@ mapc_status mapc_compute_set_force_mode(mapc_compute *c, mapc_force_mode mode)
 }
 
 // ---- the step ---------------------------------------------------------------------------------
-mapc_status mapc_compute_simulate(mapc_compute *c, int num_active_particles, float delta_time,
-                                  float damping, uint64_t consumer_fence_value)
+// Enqueues one step on the compute (and comm) stream.  Runs either straight away or, when the
+// compute stream is gated on a consumer-fence value nobody has submitted yet, when that gate opens.
+static mapc_status enqueue_step(mapc_compute *c, uint32_t b, int n_targets, int n_sources, float delta_time,
+                                float damping, mapc_force_mode mode)
 {
-    if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
-    if (num_active_particles < 0 || (uint32_t)num_active_particles > c->n)
-        return fail(MAPC_ERR_INVALID_ARGUMENT, "num_active_particles %d outside [0, %u]",
-                    num_active_particles, c->n);
-    if (!c->has_state) return fail(MAPC_ERR_INVALID_ARGUMENT, "simulate before upload/init_particles");
-    DeviceGuard g(c->device);
-
-    // Compute.cpp:1012 -- "/previous/ copy must complete before overwriting the old state"
-    if (c->consumer_fence && consumer_fence_value > 0)
-        MAPC_TRY(mapc_fence_wait_stream(c->consumer_fence, c->compute, consumer_fence_value - 1));
-
-    const uint32_t b = c->buffer_index;  // write side; read side is 1-b
-    const uint32_t r = 1u - b;
-    const int n_targets = local_targets(c, num_active_particles);
-    const int n_sources = num_active_particles;
-
+    const uint32_t r = 1u - b;  // read side (reads 1-b, writes b)
     resolve_timers(c, false);
     const int slot = (int)(c->t_next % mapc_compute::kTimerSlots);
     if (c->t_pending[slot]) resolve_timers(c, true);
     MAPC_CUDA(cudaEventRecord(c->t_begin[slot], c->compute));  // BeginTimer, Compute.cpp:1020
 
     if (n_targets > 0) {
-        if (c->mode == MAPC_FORCE_WELL) {
+        if (mode == MAPC_FORCE_WELL) {
             mapc::well_step_kernel<<<(n_targets + 255) / 256, 256, 0, c->compute>>>(
                 c->posvelo[r], c->posvelo[b], c->packed[b], (int)c->i_first, n_targets, delta_time, damping);
             MAPC_CUDA(cudaGetLastError());
@@ -655,9 +787,33 @@ mapc_status mapc_compute_simulate(mapc_compute *c, int num_active_particles, flo
         MAPC_CUDA(cudaEventRecord(c->ev_gathered[b], c->comm));
         c->gather_pending[b] = true;
     }
+    return MAPC_OK;
+}
+
+mapc_status mapc_compute_simulate(mapc_compute *c, int num_active_particles, float delta_time,
+                                  float damping, uint64_t consumer_fence_value)
+{
+    if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (num_active_particles < 0 || (uint32_t)num_active_particles > c->n)
+        return fail(MAPC_ERR_INVALID_ARGUMENT, "num_active_particles %d outside [0, %u]",
+                    num_active_particles, c->n);
+    if (!c->has_state) return fail(MAPC_ERR_INVALID_ARGUMENT, "simulate before upload/init_particles");
+    DeviceGuard g(c->device);
+
+    // Compute.cpp:1012 -- "/previous/ copy must complete before overwriting the old state"
+    if (c->consumer_fence && consumer_fence_value > 0)
+        MAPC_TRY(mapc::gs_wait(&c->gcompute, c->consumer_fence, consumer_fence_value - 1));
+
+    const uint32_t b = c->buffer_index;  // write side
+    const int n_targets = local_targets(c, num_active_particles);
+    const int n_sources = num_active_particles;
+    const mapc_force_mode mode = c->mode;
+    MAPC_TRY(mapc::gs_call(&c->gcompute, [=]() -> mapc_status {
+        return enqueue_step(c, b, n_targets, n_sources, delta_time, damping, mode);
+    }));
 
     // MoveToNextFrame, Compute.cpp:993-1004
-    MAPC_TRY(mapc_fence_signal_stream(c->fence, c->compute, c->fence_value));
+    MAPC_TRY(mapc::gs_signal(&c->gcompute, c->fence, c->fence_value));
     c->fence_value++;
     c->buffer_index = 1u - c->buffer_index;
     return MAPC_OK;
@@ -670,11 +826,15 @@ mapc_status mapc_compute_wait_for_gpu(mapc_compute *c)
     if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
     DeviceGuard g(c->device);
     // Compute.cpp:931-938: Signal(m_fenceValue); m_fenceValue++; host wait
-    for (int s = 0; s < 2; ++s)
-        if (c->gather_pending[s]) MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_gathered[s], 0));
+    MAPC_TRY(mapc::gs_call(&c->gcompute, [c]() -> mapc_status {
+        for (int s = 0; s < 2; ++s)
+            if (c->gather_pending[s]) MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_gathered[s], 0));
+        return MAPC_OK;
+    }));
     const uint64_t v = c->fence_value;
-    MAPC_TRY(mapc_fence_signal_stream(c->fence, c->compute, v));
+    MAPC_TRY(mapc::gs_signal(&c->gcompute, c->fence, v));
     c->fence_value++;
+    MAPC_TRY(mapc::require_ungated(&c->gcompute, "WaitForGpu"));
     MAPC_CUDA(cudaStreamSynchronize(c->compute));
     MAPC_CUDA(cudaStreamSynchronize(c->comm));
     if (mapc_fence_completed_value(c->fence) < v)
@@ -730,9 +890,11 @@ mapc_status mapc_compute_flush(mapc_compute *c)
 {
     if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
     DeviceGuard g(c->device);
-    for (int s = 0; s < 2; ++s)
-        if (c->gather_pending[s]) MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_gathered[s], 0));
-    return MAPC_OK;
+    return mapc::gs_call(&c->gcompute, [c]() -> mapc_status {
+        for (int s = 0; s < 2; ++s)
+            if (c->gather_pending[s]) MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_gathered[s], 0));
+        return MAPC_OK;
+    });
 }
 
 mapc_status mapc_compute_copy_state(mapc_compute *dst, mapc_compute *src)
@@ -822,6 +984,7 @@ struct mapc_consumer {
     uint32_t n = 0;
     cudaStream_t copy = nullptr;     // m_copyQueue
     cudaStream_t render = nullptr;   // m_commandQueue (direct queue): consumes the local buffer
+    mapc::GatedStream gcopy, grender;  // the same streams behind the fence gate (fence.hpp)
     float4 *local[2] = {nullptr, nullptr};   // m_buffers: positions local to the consumer's device
     float4 *host[2] = {nullptr, nullptr};    // pinned dump targets ("the screen")
     mapc_fence *copy_fence = nullptr;        // m_copyFence, shared with the producer
@@ -846,6 +1009,8 @@ mapc_status mapc_consumer_destroy(mapc_consumer *r)
 {
     if (!r) return MAPC_OK;
     DeviceGuard g(r->device);
+    mapc::gs_detach(&r->gcopy);
+    mapc::gs_detach(&r->grender);
     if (r->copy) cudaStreamSynchronize(r->copy);
     if (r->render) cudaStreamSynchronize(r->render);
     if (r->producer && r->producer->consumer_fence == r->copy_fence) r->producer->consumer_fence = nullptr;
@@ -867,10 +1032,12 @@ mapc_status mapc_consumer_wait_for_gpu(mapc_consumer *r)
     DeviceGuard g(r->device);
     // Render::WaitForGpu, Render.cpp:626-647: copy fence, then render fence, then host wait
     r->copy_fence_value++;
-    MAPC_TRY(mapc_fence_signal_stream(r->copy_fence, r->copy, r->copy_fence_value));
-    MAPC_TRY(mapc_fence_wait_stream(r->copy_fence, r->render, r->copy_fence_value));
-    MAPC_TRY(mapc_fence_signal_stream(r->render_fence, r->render, r->render_fence_value));
+    MAPC_TRY(mapc::gs_signal(&r->gcopy, r->copy_fence, r->copy_fence_value));
+    MAPC_TRY(mapc::gs_wait(&r->grender, r->copy_fence, r->copy_fence_value));
+    MAPC_TRY(mapc::gs_signal(&r->grender, r->render_fence, r->render_fence_value));
     r->render_fence_value++;
+    MAPC_TRY(mapc::require_ungated(&r->gcopy, "consumer WaitForGpu (copy stream)"));
+    MAPC_TRY(mapc::require_ungated(&r->grender, "consumer WaitForGpu (render stream)"));
     MAPC_CUDA(cudaStreamSynchronize(r->copy));
     MAPC_CUDA(cudaStreamSynchronize(r->render));
     return MAPC_OK;
@@ -896,6 +1063,9 @@ mapc_status mapc_consumer_create(mapc_consumer **out, mapc_compute *producer, in
     auto body = [&]() -> mapc_status {
         MAPC_CUDA(cudaStreamCreateWithFlags(&r->copy, cudaStreamNonBlocking));
         MAPC_CUDA(cudaStreamCreateWithFlags(&r->render, cudaStreamNonBlocking));
+        r->gcopy.stream = r->copy;
+        r->grender.stream = r->render;
+        r->gcopy.device = r->grender.device = device;
         for (int i = 0; i < 2; ++i) {
             MAPC_CUDA(cudaMalloc(&r->local[i], (size_t)r->n * sizeof(float4)));
             MAPC_CUDA(cudaHostAlloc(&r->host[i], (size_t)r->n * sizeof(float4), cudaHostAllocPortable));
@@ -941,45 +1111,80 @@ mapc_status mapc_consumer_draw(mapc_consumer *r, int num_active_particles, uint6
 
     // ---- CopySimulationResults(in_fenceValue, in_numParticlesCopied), Render.cpp:789-831 ---------
     // wait on the previous frame's render to finish with the local buffer (:796)
-    MAPC_TRY(mapc_fence_wait_stream(r->render_fence, r->copy, r->render_fence_value - 1));
+    MAPC_TRY(mapc::gs_wait(&r->gcopy, r->render_fence, r->render_fence_value - 1));
     const uint32_t src_shared = 1u - r->shared_buffer_index;   // :798
     const uint32_t dst_local = 1u - r->current_buffer_index;   // :799
     r->shared_buffer_index = 1u - r->shared_buffer_index;      // :800
-    if (num_particles_copied > 0)                              // :814 copy just the particles required
-        MAPC_CUDA(cudaMemcpyPeerAsync(r->local[dst_local], r->device, r->producer->packed[src_shared],
-                                      r->producer->device, (size_t)num_particles_copied * sizeof(float4),
-                                      r->copy));
+    if (num_particles_copied > 0) {                            // :814 copy just the particles required
+        float4 *dst = r->local[dst_local];
+        const float4 *src = r->producer->packed[src_shared];
+        const int dst_dev = r->device, src_dev = r->producer->device;
+        const size_t bytes = (size_t)num_particles_copied * sizeof(float4);
+        cudaStream_t copy = r->copy;
+        MAPC_TRY(mapc::gs_call(&r->gcopy, [=]() -> mapc_status {
+            MAPC_CUDA(cudaMemcpyPeerAsync(dst, dst_dev, src, src_dev, bytes, copy));
+            return MAPC_OK;
+        }));
+    }
     r->local_frame[dst_local] = r->copies++;   // results of the PREVIOUS Simulate (step number = copies so far)
-    // don't start the next copy until the compute device has produced new results (:826)
-    MAPC_TRY(mapc_fence_wait_stream(r->compute_fence, r->copy, compute_fence_value));
+    // don't start the next copy until the compute device has produced new results (:826).  The value
+    // belongs to the Simulate that is submitted AFTER this call: the copy stream gates here (fence.hpp).
+    MAPC_TRY(mapc::gs_wait(&r->gcopy, r->compute_fence, compute_fence_value));
     r->copy_fence_value++;                                     // :829-830
-    MAPC_TRY(mapc_fence_signal_stream(r->copy_fence, r->copy, r->copy_fence_value));
+    MAPC_TRY(mapc::gs_signal(&r->gcopy, r->copy_fence, r->copy_fence_value));
 
     // ---- the "draw" of local[m_currentBufferIndex] (:884-891): headless = dump to pinned host ------
     const uint32_t cur = r->current_buffer_index;
     r->current_buffer_index = 1u - r->current_buffer_index;    // :885
     const uint32_t slot = r->frame_index;
-    if (num_active_particles > 0)
-        MAPC_CUDA(cudaMemcpyAsync(r->host[slot], r->local[cur], (size_t)num_active_particles * sizeof(float4),
-                                  cudaMemcpyDeviceToHost, r->render));
+    if (num_active_particles > 0) {
+        float4 *dst = r->host[slot];
+        const float4 *src = r->local[cur];
+        const size_t bytes = (size_t)num_active_particles * sizeof(float4);
+        cudaStream_t render = r->render;
+        MAPC_TRY(mapc::gs_call(&r->grender, [=]() -> mapc_status {
+            MAPC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, render));
+            return MAPC_OK;
+        }));
+    }
     r->host_frame[slot] = r->local_frame[cur];
     r->host_count[slot] = (uint32_t)num_active_particles;
 
     // render waits for this frame's copy; hand the copy fence value to the producer (:925-926)
-    MAPC_TRY(mapc_fence_wait_stream(r->copy_fence, r->render, r->copy_fence_value));
+    MAPC_TRY(mapc::gs_wait(&r->grender, r->copy_fence, r->copy_fence_value));
     *inout_fence_value = r->copy_fence_value;
 
     // ---- MoveToNextFrame, Render.cpp:653-677 ---------------------------------------------------------
     r->frame_fence_values[r->frame_index] = r->render_fence_value;
     r->host_fence[slot] = r->render_fence_value;
-    MAPC_TRY(mapc_fence_signal_stream(r->render_fence, r->render, r->render_fence_value));
+    MAPC_TRY(mapc::gs_signal(&r->grender, r->render_fence, r->render_fence_value));
     r->render_fence_value++;
     r->frame_index = 1u - r->frame_index;                      // two "back buffers"
     r->frames_drawn++;
     // "If the next frame is not ready to be rendered yet, wait until it is ready" (:665-674; the
     // reference returns the event and Particles::Draw waits on it, Particles.cpp:452-456)
-    if (mapc_fence_completed_value(r->render_fence) < r->frame_fence_values[r->frame_index])
-        MAPC_TRY(mapc_fence_wait_host(r->render_fence, r->frame_fence_values[r->frame_index], 60000));
+    const uint64_t throttle = r->frame_fence_values[r->frame_index];
+    if (mapc_fence_completed_value(r->render_fence) < throttle) {
+        if (r->render_fence->submitted < throttle)
+            return fail(MAPC_ERR_TIMEOUT,
+                        "Draw called twice without the Simulate in between: render fence value %llu waits for "
+                        "a compute fence value nobody has submitted", (unsigned long long)throttle);
+        MAPC_TRY(mapc_fence_wait_host(r->render_fence, throttle, 60000));
+    }
+    return MAPC_OK;
+}
+
+mapc_status mapc_consumer_counters(const mapc_consumer *r, uint64_t out[8])
+{
+    if (!r || !out) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
+    out[0] = mapc_fence_completed_value(r->copy_fence);
+    out[1] = r->copy_fence_value;
+    out[2] = mapc_fence_completed_value(r->render_fence);
+    out[3] = r->render_fence_value;
+    out[4] = r->shared_buffer_index;
+    out[5] = r->current_buffer_index;
+    out[6] = r->frames_drawn;
+    out[7] = r->copies;
     return MAPC_OK;
 }
 

@@ -33,7 +33,7 @@ def allpairs(name, inp, steps, dt, damping):
 
 
 def main():
-    allpairs("sphere_1000", pkg.ic.uniform_sphere(1000, 600.0, seed=7, speed=2.0), 10, 0.1, 1.0)
+    allpairs("lattice_1000", pkg.ic.lattice_sphere(1000, 900.0, seed=7, speed=2.0), 10, 0.1, 1.0)
     allpairs("plummer_777", pkg.ic.plummer(777, 500.0, seed=8, velocity_scale=0.1), 10, 0.05, 0.995)
     w = pkg.ic.uniform_sphere(1000, 400.0, seed=9, speed=15.0)
     out = orc.step_well(w, dt=0.1, damping=1.0)

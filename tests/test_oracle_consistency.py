@@ -55,7 +55,7 @@ def test_n_active_leaves_tail_untouched(oracle, mapc):
     assert out[128:].tobytes() == stale[128:].tobytes()
 
 
-@pytest.mark.parametrize("name", ["sphere_1000", "plummer_777", "well_1000"])
+@pytest.mark.parametrize("name", ["lattice_1000", "plummer_777", "well_1000"])
 def test_golden_fixtures(oracle, name):
     path = os.path.join(GOLDEN, name + ".npz")
     assert os.path.exists(path), "golden fixture missing: run tests/golden/make_golden.py"
