@@ -213,6 +213,8 @@ def run_mapc(args) -> None:
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def l2_flush():
+        if args.no_l2_flush:
+            return
         with torch.cuda.stream(stream):
             flush_buf.zero_()
 
@@ -299,7 +301,10 @@ def run_mapc(args) -> None:
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"allpairs uniform sphere N={n} seed={SEED} dt={DT} damping={DAMPING}",
                        "n": n, "n_per_gpu": c.num_local, "plan": c.Plan(), "parallelism": f"i-shard x{world}",
-                       "l2": "256 MiB memset between timed steps (inside the bracket)"},
+                       "l2": "no flush (latency run)" if args.no_l2_flush else
+                             "256 MiB memset between timed steps (inside the bracket)"},
+            "step_us": {"min": float(step_ms.min() * 1e3), "median": float(np.median(step_ms) * 1e3),
+                        "p99": float(np.percentile(step_ms, 99) * 1e3), "samples": int(step_ms.size)} if step_ms.size else None,
             "tflops_at_20flop": value * FLOP_PER_INTERACTION / 1e3,
             "frac_fp32_peak": value * FLOP_PER_INTERACTION / 1e3 / (peak_tflops * world),
             "roofline": roofline, "cpu_baseline": cpu,
@@ -325,6 +330,8 @@ def main() -> None:
     ap.add_argument("--n", type=int, default=None, help="override the number of bodies")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-l2-flush", action="store_true",
+                    help="latency runs (N = 10,000, config 2): no 256 MiB memset between steps")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3:
