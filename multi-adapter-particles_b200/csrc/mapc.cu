@@ -279,8 +279,8 @@ namespace {
 struct Plan {
     int pairs;    // P: register pairs per thread (2P targets per thread)
     int threads;  // T
-    int blocks_x;
-    int segments;
+    int blocks_x; // target blocks of T*2P bodies
+    int segments; // canonical S
 };
 
 int env_int(const char *name, int dflt)
@@ -289,24 +289,36 @@ int env_int(const char *name, int dflt)
     return (v && *v) ? atoi(v) : dflt;
 }
 
-// Finer target blocks when there is little work so every SM gets several waves; the choice
-// changes neither the arithmetic nor its order (only S does), so it is free to vary.
+// Launch shapes (P, T) with the FMA-pipe efficiency each reaches at large N (tools/ubench,
+// profiles/): all sit on the same 67-72 % plateau, so at large N the choice barely matters, while
+// at small N what decides is how evenly the cells fall on the 4 x SMs warp schedulers and how many
+// target lanes the last block leaves idle.  The shape changes neither the arithmetic nor its order
+// (only S does), so it is free to vary with N, the shard size and the device.
+struct Shape { int pairs, threads; float efficiency; };
+constexpr Shape kShapes[6] = {{4, 256, 0.717f}, {4, 128, 0.715f}, {2, 128, 0.713f},
+                              {2, 64, 0.700f},  {1, 64, 0.680f},  {1, 32, 0.668f}};
+
 Plan make_plan(int n_targets, int n_sources, int sm_count)
 {
     const int S = mapc_plan_segments((uint32_t)n_sources);
-    const int cand[5][2] = {{4, 256}, {4, 128}, {2, 128}, {1, 128}, {1, 64}};
-    Plan best{1, 64, 0, S};
+    Plan best{1, 32, 0, S};
+    float best_score = -1.f;
     const int fp = env_int("MAPC_PLAN_PAIRS", 0), ft = env_int("MAPC_PLAN_THREADS", 0);
-    for (int c = 0; c < 5; ++c) {
-        const int P = cand[c][0], T = cand[c][1];
-        const int per_block = T * 2 * P;
+    for (const Shape &sh : kShapes) {
+        if ((fp && fp != sh.pairs) || (ft && ft != sh.threads)) continue;
+        const int per_block = sh.threads * 2 * sh.pairs;
         const int bx = (n_targets + per_block - 1) / per_block;
-        best = Plan{P, T, bx, S};
-        if (fp || ft) {
-            if ((!fp || fp == P) && (!ft || ft == T)) break;
-            continue;
+        if (bx == 0) continue;
+        const double used = (double)n_targets / ((double)bx * per_block);            // busy target lanes
+        const double blocks_per_sm = (double)bx * S / sm_count;
+        const double warps_per_smsp = blocks_per_sm * (sh.threads / 32) / 4.0;
+        const double bal_block = blocks_per_sm / std::ceil(blocks_per_sm);
+        const double bal_warp = warps_per_smsp / std::ceil(warps_per_smsp);
+        const float score = (float)(sh.efficiency * used * std::min(bal_block, bal_warp));
+        if (score > best_score) {
+            best_score = score;
+            best = Plan{sh.pairs, sh.threads, bx, S};
         }
-        if ((long long)bx * S >= 6LL * sm_count) break;
     }
     return best;
 }
@@ -330,6 +342,8 @@ struct mapc_compute {
     float4 *packed[2] = {nullptr, nullptr};         // packed positions, all N, per side
     float4 *partial = nullptr;                      // [segments][n_local]
     int partial_segments = 0;
+    unsigned *counters = nullptr;                   // per target block: segments finished this step
+    int counters_key = 0;                           // block size the counters were last used with
 
     mapc_fence *fence = nullptr;            // m_fence
     mapc_fence *consumer_fence = nullptr;   // m_sharedRenderFence (borrowed)
@@ -378,34 +392,27 @@ void resolve_timers(mapc_compute *c, bool block)
     }
 }
 
-// Launch shapes measured on B200 at N = 262,144 (tools/ubench, profiles/r01_ubench_shapes.txt):
-// all sit on the same 70-72 % plateau, so the choice is about wave quantisation, not the inner loop.
-template <int P, int T, int U, int MINB, int ORDER>
-mapc_status launch_force(mapc_compute *c, const float4 *pos, int n_targets, int n_sources, int S,
-                         const mapc::SegList &segs, int blocks_x)
+// grid = (target blocks, segments of this launch): one cell per thread block
+template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE>
+mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args)
 {
-    if (segs.count == 0 || n_targets <= 0) return MAPC_OK;
-    dim3 grid((unsigned)blocks_x, (unsigned)segs.count, 1);
-    mapc::force_segments_kernel<P, T, U, MINB, ORDER><<<grid, T, 0, c->compute>>>(
-        pos, c->partial, (int)c->i_first, n_targets, n_sources, S, segs, (int)c->n_local);
+    dim3 grid((unsigned)args.n_iblocks, (unsigned)args.segs.count, 1);
+    mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE><<<grid, T, 0, c->compute>>>(args);
     MAPC_CUDA(cudaGetLastError());
     ++c->launches;
     return MAPC_OK;
 }
 
-mapc_status launch_force_plan(mapc_compute *c, const Plan &pl, const float4 *pos, int n_targets,
-                              int n_sources, const mapc::SegList &segs)
+template <bool FUSE>
+mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::StepArgs &args)
 {
-    const int S = pl.segments;
-    if (pl.pairs == 4 && pl.threads == 256)
-        return launch_force<4, 256, 8, 2, 0>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
-    if (pl.pairs == 4 && pl.threads == 128)
-        return launch_force<4, 128, 8, 4, 0>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
-    if (pl.pairs == 2 && pl.threads == 128)
-        return launch_force<2, 128, 4, 4, 2>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
-    if (pl.pairs == 1 && pl.threads == 128)
-        return launch_force<1, 128, 8, 8, 0>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
-    return launch_force<1, 64, 8, 8, 0>(c, pos, n_targets, n_sources, S, segs, pl.blocks_x);
+    if (args.segs.count == 0 || args.i_cnt <= 0) return MAPC_OK;
+    if (pl.pairs == 4 && pl.threads == 256) return launch_force<4, 256, 256, 8, 2, 0, FUSE>(c, args);
+    if (pl.pairs == 4 && pl.threads == 128) return launch_force<4, 128, 256, 8, 4, 0, FUSE>(c, args);
+    if (pl.pairs == 2 && pl.threads == 128) return launch_force<2, 128, 256, 4, 4, 2, FUSE>(c, args);
+    if (pl.pairs == 2 && pl.threads == 64) return launch_force<2, 64, 64, 4, 8, 2, FUSE>(c, args);
+    if (pl.pairs == 1 && pl.threads == 64) return launch_force<1, 64, 64, 8, 16, 0, FUSE>(c, args);
+    return launch_force<1, 32, 64, 8, 32, 0, FUSE>(c, args);
 }
 
 // targets of this shard that a Simulate(n_active) updates, as a count from i_first
@@ -478,6 +485,8 @@ mapc_status create_common(mapc_compute **out, uint32_t n, int device, int rank, 
             MAPC_CUDA(cudaEventCreate(&c->t_end[k]));
         }
         MAPC_TRY(ensure_partial(c, mapc_plan_segments(n)));
+        MAPC_CUDA(cudaMalloc(&c->counters, ((size_t)c->n_local / 64 + 2) * sizeof(unsigned)));
+        MAPC_CUDA(cudaMemset(c->counters, 0, ((size_t)c->n_local / 64 + 2) * sizeof(unsigned)));
         // Compute.cpp:434-436: fence created with value 0, m_fenceValue++ -> 1
         MAPC_TRY(mapc_fence_create(&c->fence, c->fence_value));
         c->fence_value++;
@@ -654,6 +663,7 @@ mapc_status mapc_compute_destroy(mapc_compute *c)
         if (c->ev_gathered[s]) cudaEventDestroy(c->ev_gathered[s]);
     }
     if (c->partial) cudaFree(c->partial);
+    if (c->counters) cudaFree(c->counters);
     if (c->ev_integrated) cudaEventDestroy(c->ev_integrated);
     for (int k = 0; k < mapc_compute::kTimerSlots; ++k) {
         if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]);
@@ -751,8 +761,29 @@ static mapc_status enqueue_step(mapc_compute *c, uint32_t b, int n_targets, int 
         } else {
             const Plan pl = make_plan(n_targets, n_sources, c->sm_count);
             MAPC_TRY(ensure_partial(c, pl.segments));
+            const bool fuse = env_int("MAPC_FUSE", 1) != 0;
+            const int key = pl.pairs * 1024 + pl.threads;
+            if (fuse && c->counters_key != key) {  // arrival counters are per target block of this shape
+                MAPC_CUDA(cudaMemsetAsync(c->counters, 0, ((size_t)c->n_local / 64 + 2) * sizeof(unsigned), c->compute));
+                c->counters_key = key;
+            }
             // segments whose sources all live in this shard are resident already (this rank wrote
             // them in its own integrate pass); the others need the all-gather of side r.
+            mapc::StepArgs args{};
+            args.pos = c->packed[r];
+            args.partial = c->partial;
+            args.partial_stride = (int)c->n_local;
+            args.i_first = (int)c->i_first;
+            args.i_cnt = n_targets;
+            args.n_sources = n_sources;
+            args.S = pl.segments;
+            args.n_iblocks = pl.blocks_x;
+            args.counters = c->counters;
+            args.in = c->posvelo[r];
+            args.out = c->posvelo[b];
+            args.pos_next = c->packed[b];
+            args.dt = delta_time;
+            args.damping = damping;
             mapc::SegList local{0, {}}, remote{0, {}};
             for (int s = 0; s < pl.segments; ++s) {
                 int j0, j1;
@@ -761,16 +792,20 @@ static mapc_status enqueue_step(mapc_compute *c, uint32_t b, int n_targets, int 
                                       (j0 >= (int)c->i_first && j1 <= (int)(c->i_first + c->n_local));
                 (is_local ? local : remote).ids[(is_local ? local : remote).count++] = s;
             }
-            MAPC_TRY(launch_force_plan(c, pl, c->packed[r], n_targets, n_sources, local));
+            args.segs = local;
+            MAPC_TRY(fuse ? launch_force_shape<true>(c, pl, args) : launch_force_shape<false>(c, pl, args));
             if (remote.count > 0) {
                 MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_gathered[r], 0));
-                MAPC_TRY(launch_force_plan(c, pl, c->packed[r], n_targets, n_sources, remote));
+                args.segs = remote;
+                MAPC_TRY(fuse ? launch_force_shape<true>(c, pl, args) : launch_force_shape<false>(c, pl, args));
             }
-            mapc::integrate_kernel<<<(n_targets + 255) / 256, 256, 0, c->compute>>>(
-                c->posvelo[r], c->posvelo[b], c->packed[b], c->partial, (int)c->n_local, pl.segments,
-                (int)c->i_first, n_targets, delta_time, damping);
-            MAPC_CUDA(cudaGetLastError());
-            ++c->launches;
+            if (!fuse) {
+                mapc::integrate_kernel<<<(n_targets + 255) / 256, 256, 0, c->compute>>>(
+                    c->posvelo[r], c->posvelo[b], c->packed[b], c->partial, (int)c->n_local, pl.segments,
+                    (int)c->i_first, n_targets, delta_time, damping);
+                MAPC_CUDA(cudaGetLastError());
+                ++c->launches;
+            }
         }
     }
     MAPC_CUDA(cudaEventRecord(c->t_end[slot], c->compute));  // EndTimer, Compute.cpp:1046

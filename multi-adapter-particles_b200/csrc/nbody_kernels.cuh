@@ -138,117 +138,6 @@ __device__ __forceinline__ void group_interaction(const float4 b, const float2 *
     }
 }
 
-// One block = T threads x 2P targets against one canonical segment of sources.
-//   pos            packed float4 positions, global indexing (targets and sources)
-//   partial        [S][partial_stride] float4, local target indexing
-//   i_first/i_cnt  local targets are bodies [i_first, i_first + i_cnt)
-// U = unroll of the source loop, MINB = resident blocks per SM asked of ptxas (register cap).
-// Neither P, T, U nor MINB changes any rounding: each target's chain is the same ops in the
-// same ascending-j order.
-template <int P, int T, int U, int MINB, int ORDER = 0>
-__global__ void __launch_bounds__(T, MINB)
-force_segments_kernel(const float4 *__restrict__ pos, float4 *__restrict__ partial, int i_first,
-                      int i_cnt, int n_sources, int S, SegList segs, int partial_stride)
-{
-    constexpr int kLoads = kTileBodies / T;  // staging loads per thread per tile
-    static_assert(kTileBodies % T == 0, "tile must be a multiple of the block size");
-    __shared__ float4 tile[2][kTileBodies];
-
-    const int tid = threadIdx.x;
-    const int seg = segs.ids[blockIdx.y];
-    int j0, j1;
-    segment_range(n_sources, S, seg, j0, j1);
-
-    // targets: thread owns local bodies i_block + q*T + tid, q = 0..2P-1 (coalesced in q);
-    // pair p = (q = 2p, q = 2p+1).  Out-of-range lanes are clamped and never stored.
-    const int i_block = blockIdx.x * (T * 2 * P);
-    float2 nxi[P], nyi[P], nzi[P], ax[P], ay[P], az[P];
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        int ia = i_block + (2 * p) * T + tid;
-        int ib = i_block + (2 * p + 1) * T + tid;
-        ia = ia < i_cnt ? ia : i_cnt - 1;
-        ib = ib < i_cnt ? ib : i_cnt - 1;
-        const float4 a = pos[i_first + ia];
-        const float4 b = pos[i_first + ib];
-        nxi[p] = make_float2(-a.x, -b.x);
-        nyi[p] = make_float2(-a.y, -b.y);
-        nzi[p] = make_float2(-a.z, -b.z);
-        ax[p] = ay[p] = az[p] = make_float2(0.f, 0.f);
-    }
-
-    const int n_tiles = (j1 - j0 + kTileBodies - 1) / kTileBodies;
-    float4 stage[kLoads];
-
-    // prologue: tile 0 -> smem buffer 0
-    if (n_tiles > 0) {
-#pragma unroll
-        for (int l = 0; l < kLoads; ++l) {
-            const int j = j0 + l * T + tid;
-            stage[l] = j < j1 ? pos[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int l = 0; l < kLoads; ++l) tile[0][l * T + tid] = stage[l];
-    }
-    __syncthreads();
-
-    for (int t = 0; t < n_tiles; ++t) {
-        const int buf = t & 1;
-        const int jt = j0 + t * kTileBodies;
-        const bool has_next = (t + 1) < n_tiles;
-        // prefetch the next tile into registers while this one is consumed
-        if (has_next) {
-#pragma unroll
-            for (int l = 0; l < kLoads; ++l) {
-                const int j = jt + kTileBodies + l * T + tid;
-                stage[l] = j < j1 ? pos[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        const int cnt = (j1 - jt) < kTileBodies ? (j1 - jt) : kTileBodies;
-        if (cnt == kTileBodies) {
-            constexpr int kU = U;
-#pragma unroll kU
-            for (int j = 0; j < kTileBodies; ++j) {
-                const float4 b = tile[buf][j];
-                if (ORDER == 2) {
-                    group_interaction<P>(b, nxi, nyi, nzi, ax, ay, az);
-                } else {
-#pragma unroll
-                    for (int p = 0; p < P; ++p)
-                        pair_interaction<ORDER == 1>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
-                }
-            }
-        } else {
-            // ragged last tile of the segment: loop bounded at the real count, no phantom bodies
-#pragma unroll 1
-            for (int j = 0; j < cnt; ++j) {
-                const float4 b = tile[buf][j];
-                if (ORDER == 2) {
-                    group_interaction<P>(b, nxi, nyi, nzi, ax, ay, az);
-                } else {
-#pragma unroll
-                    for (int p = 0; p < P; ++p)
-                        pair_interaction<ORDER == 1>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
-                }
-            }
-        }
-        if (has_next) {
-#pragma unroll
-            for (int l = 0; l < kLoads; ++l) tile[buf ^ 1][l * T + tid] = stage[l];
-        }
-        __syncthreads();
-    }
-
-    float4 *out = partial + (size_t)seg * partial_stride;
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        const int ia = i_block + (2 * p) * T + tid;
-        const int ib = i_block + (2 * p + 1) * T + tid;
-        if (ia < i_cnt) out[ia] = make_float4(ax[p].x, ay[p].x, az[p].x, 0.f);
-        if (ib < i_cnt) out[ib] = make_float4(ax[p].y, ay[p].y, az[p].y, 0.f);
-    }
-}
-
 // nBodyGravityCS.hlsl:103-108 with the contractions pinned (the CPU oracle's MIRRORED flavour
 // uses the same fmaf placement):
 //   vel += accel*dt (:103) FFMA; vel *= damping (:104) FMUL; pos += vel*dt (:105) FFMA;
@@ -269,6 +158,166 @@ __device__ __forceinline__ void integrate_body(const float4 pos_in, const float4
     pos_out.z = __fmaf_rn(vz, dt, pos_in.z);
     pos_out.w = __fsqrt_rn(__fmaf_rn(az, az, __fmaf_rn(ay, ay, __fmul_rn(ax, ax))));
     vel_out = make_float4(vx, vy, vz, 0.f);
+}
+
+// Everything one launch of the force kernel needs (passed by value).
+struct StepArgs {
+    const float4 *pos;         // packed positions of the read side, global indexing (targets and sources)
+    float4 *partial;           // [S][partial_stride] float4, local target indexing
+    int partial_stride;
+    int i_first, i_cnt;        // local targets are bodies [i_first, i_first + i_cnt)
+    int n_sources, S;          // canonical segmentation of the sources
+    SegList segs;              // the segments this launch evaluates
+    int n_iblocks;             // target blocks of T*2P bodies
+    // fused combine + integrate (FUSE): the block that completes the last segment of a target block
+    // sums its S partials in canonical order and applies the integration step
+    unsigned *counters;        // [n_iblocks] arrivals, zero between steps
+    const mapc_posvelo *in;    // PosVelo read side (local indexing)
+    mapc_posvelo *out;         // PosVelo write side
+    float4 *pos_next;          // packed positions of the write side (global indexing)
+    float dt, damping;
+};
+
+// Force kernel.  Work is cut into cells = (target block of T*2P bodies) x (canonical segment); one
+// thread block evaluates one cell: blockIdx.x = target block, blockIdx.y = index into args.segs.  (A
+// persistent variant that walked several cells per block was measured 25 % slower: with the targets
+// reloaded inside a loop ptxas re-pairs them with ~170 MOVs per 8 sources instead of keeping the
+// register pairs live.)  A thread owns 2P targets as P register pairs and streams the segment's
+// sources through shared memory in stages of TJ bodies (register prefetch of the next stage, one
+// barrier per stage); the math runs in 64-body tiles -- the reference tile (Particles/defines.h:37)
+// -- so only the globally last tile is ever ragged.
+// U = unroll of the source loop, MINB = resident blocks per SM asked of ptxas.  None of P, T, TJ, U,
+// MINB or ORDER changes a rounding: each target's chain is the same ops in ascending j.
+template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE>
+__global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_constant__ StepArgs a)
+{
+    constexpr int kLoads = TJ / T;  // staging loads per thread per stage
+    static_assert(TJ % T == 0 && TJ % MAPC_BLOCK_SIZE == 0, "stage must be a multiple of block and tile size");
+    __shared__ float4 tile[2][TJ];
+    __shared__ int s_is_last;
+
+    const int tid = threadIdx.x;
+    const float4 *__restrict__ pos = a.pos;
+    {
+        const int ib = blockIdx.x;
+        const int seg = a.segs.ids[blockIdx.y];
+        int j0, j1;
+        segment_range(a.n_sources, a.S, seg, j0, j1);
+
+        // targets: thread owns local bodies i_block + q*T + tid, q = 0..2P-1 (coalesced in q);
+        // pair p = (q = 2p, q = 2p+1).  Out-of-range lanes are clamped and never stored.
+        const int i_block = ib * (T * 2 * P);
+        float2 nxi[P], nyi[P], nzi[P], ax[P], ay[P], az[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            int ia = i_block + (2 * p) * T + tid;
+            int ib2 = i_block + (2 * p + 1) * T + tid;
+            ia = ia < a.i_cnt ? ia : a.i_cnt - 1;
+            ib2 = ib2 < a.i_cnt ? ib2 : a.i_cnt - 1;
+            const float4 ta = pos[a.i_first + ia];
+            const float4 tb = pos[a.i_first + ib2];
+            nxi[p] = make_float2(-ta.x, -tb.x);
+            nyi[p] = make_float2(-ta.y, -tb.y);
+            nzi[p] = make_float2(-ta.z, -tb.z);
+            ax[p] = ay[p] = az[p] = make_float2(0.f, 0.f);
+        }
+
+        const int n_stages = (j1 - j0 + TJ - 1) / TJ;
+        float4 stage[kLoads];
+        if (n_stages > 0) {  // prologue: stage 0 -> smem buffer 0
+#pragma unroll
+            for (int l = 0; l < kLoads; ++l) {
+                const int j = j0 + l * T + tid;
+                stage[l] = j < j1 ? pos[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int l = 0; l < kLoads; ++l) tile[0][l * T + tid] = stage[l];
+        }
+        __syncthreads();
+
+        for (int t = 0; t < n_stages; ++t) {
+            const int buf = t & 1;
+            const int jt = j0 + t * TJ;
+            const bool has_next = (t + 1) < n_stages;
+            if (has_next) {  // prefetch the next stage into registers while this one is consumed
+#pragma unroll
+                for (int l = 0; l < kLoads; ++l) {
+                    const int j = jt + TJ + l * T + tid;
+                    stage[l] = j < j1 ? pos[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            const int cnt = (j1 - jt) < TJ ? (j1 - jt) : TJ;
+            const int full = cnt & ~(MAPC_BLOCK_SIZE - 1);  // whole 64-body tiles of this stage
+            for (int jb = 0; jb < full; jb += MAPC_BLOCK_SIZE) {
+                constexpr int kU = U;
+#pragma unroll kU
+                for (int j = 0; j < MAPC_BLOCK_SIZE; ++j) {
+                    const float4 b = tile[buf][jb + j];
+                    if (ORDER == 2) {
+                        group_interaction<P>(b, nxi, nyi, nzi, ax, ay, az);
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < P; ++p)
+                            pair_interaction<false>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+                    }
+                }
+            }
+            // ragged tail (only the last tile of all sources): bounded at the real count, no phantom bodies
+#pragma unroll 1
+            for (int j = full; j < cnt; ++j) {
+                const float4 b = tile[buf][j];
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+                    pair_interaction<false>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+            }
+            if (has_next) {
+#pragma unroll
+                for (int l = 0; l < kLoads; ++l) tile[buf ^ 1][l * T + tid] = stage[l];
+            }
+            __syncthreads();
+        }
+
+        float4 *out = a.partial + (size_t)seg * a.partial_stride;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int ia = i_block + (2 * p) * T + tid;
+            const int ib2 = i_block + (2 * p + 1) * T + tid;
+            if (ia < a.i_cnt) out[ia] = make_float4(ax[p].x, ay[p].x, az[p].x, 0.f);
+            if (ib2 < a.i_cnt) out[ib2] = make_float4(ax[p].y, ay[p].y, az[p].y, 0.f);
+        }
+
+        if (FUSE) {
+            // last arrival for this target block combines and integrates (fixed order: any block may do it)
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) s_is_last = (atomicAdd(&a.counters[ib], 1u) + 1u == (unsigned)a.S);
+            __syncthreads();
+            if (s_is_last) {
+                __threadfence();
+#pragma unroll
+                for (int q = 0; q < 2 * P; ++q) {
+                    const int i = i_block + q * T + tid;
+                    if (i < a.i_cnt) {
+                        float sx = 0.f, sy = 0.f, sz = 0.f;
+                        for (int s = 0; s < a.S; ++s) {
+                            const float4 pp = __ldcg(a.partial + (size_t)s * a.partial_stride + i);
+                            sx = __fadd_rn(sx, pp.x);
+                            sy = __fadd_rn(sy, pp.y);
+                            sz = __fadd_rn(sz, pp.z);
+                        }
+                        const float4 *src = reinterpret_cast<const float4 *>(a.in + i);
+                        float4 pos_out, vel_out;
+                        integrate_body(src[0], src[1], sx, sy, sz, a.dt, a.damping, pos_out, vel_out);
+                        float4 *dst = reinterpret_cast<float4 *>(a.out + i);
+                        dst[0] = pos_out;
+                        dst[1] = vel_out;
+                        a.pos_next[a.i_first + i] = pos_out;
+                    }
+                }
+                if (tid == 0) a.counters[ib] = 0u;  // ready for the next step
+            }
+        }
+    }
 }
 
 // Sum the S segment partials left to right, integrate, write side b and the packed mirror.

@@ -216,18 +216,23 @@ def test_copy_state_and_migration_ctor(mapc, oracle, gpu):
 
 
 def test_launch_geometry_does_not_change_bits(mapc, gpu):
-    """P (pairs/thread) and T (block size) only regroup targets: results must be bit-identical."""
+    """P (pairs/thread) and T (block size) only regroup targets, and the fused combine+integrate is
+    the same arithmetic as the separate integrate kernel: results must be bit-identical."""
     n = 5000
     p = gentle_sphere(mapc, n, seed=13, speed=1.0)
     base = gpu_steps(mapc, p, 2)
     try:
-        for pairs, threads in ((4, 256), (4, 128), (2, 128), (1, 128), (1, 64)):
+        os.environ["MAPC_FUSE"] = "0"
+        assert gpu_steps(mapc, p, 2).tobytes() == base.tobytes(), "unfused path differs"
+        os.environ.pop("MAPC_FUSE")
+        for pairs, threads in ((4, 256), (4, 128), (2, 128), (2, 64), (1, 64), (1, 32)):
             os.environ["MAPC_PLAN_PAIRS"], os.environ["MAPC_PLAN_THREADS"] = str(pairs), str(threads)
             with mapc.Compute(n, 0) as c:
                 plan = c.Plan()
                 assert (plan["pairs_per_thread"], plan["threads_per_block"]) == (pairs, threads)
             assert gpu_steps(mapc, p, 2).tobytes() == base.tobytes(), (pairs, threads)
     finally:
+        os.environ.pop("MAPC_FUSE", None)
         os.environ.pop("MAPC_PLAN_PAIRS", None)
         os.environ.pop("MAPC_PLAN_THREADS", None)
 
@@ -257,7 +262,7 @@ def test_gpu_timer_and_launch_counter(mapc, gpu):
         for _ in range(8):
             c.Simulate(n, 0)
         c.WaitForGpu()
-        assert c.KernelLaunches() == before + 16      # force + integrate per step
+        assert c.KernelLaunches() == before + 8       # one fused force+integrate kernel per step
         times, last_ms = c.GetGpuTimes()
         assert times[0][1] == "simulate ms" and times[0][0] > 0 and last_ms > 0
 

@@ -9,6 +9,7 @@
 // Build: make -C tools   Run: tools/ubench [N]
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -153,24 +154,33 @@ struct Timer {
 static int g_sms = 148;
 static double g_peak_tflops = 74.45;
 
-template <int P, int T, int U, int MINB, int SA = 0>
+template <int P, int T, int TJ, int U, int MINB, int ORDER = 0>
 void run_force(const float4 *pos, float4 *partial, int n, Timer &t)
 {
     const int S = 8;
-    mapc::SegList segs{S, {}};
-    for (int s = 0; s < S; ++s) segs.ids[s] = s;
+    mapc::StepArgs args{};
+    args.pos = pos;
+    args.partial = partial;
+    args.partial_stride = n;
+    args.i_first = 0;
+    args.i_cnt = n;
+    args.n_sources = n;
+    args.S = S;
+    args.segs.count = S;
+    for (int s = 0; s < S; ++s) args.segs.ids[s] = s;
     const int per_block = T * 2 * P;
-    dim3 grid((n + per_block - 1) / per_block, S);
+    args.n_iblocks = (n + per_block - 1) / per_block;
+    auto kernel = mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, false>;
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mapc::force_segments_kernel<P, T, U, MINB, SA>, T, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, T, 0));
     cudaFuncAttributes fa;
-    CK(cudaFuncGetAttributes(&fa, mapc::force_segments_kernel<P, T, U, MINB, SA>));
-    const float ms = t.best([&] {
-        mapc::force_segments_kernel<P, T, U, MINB, SA><<<grid, T>>>(pos, partial, 0, n, n, S, segs, n);
-    }, 4);
+    CK(cudaFuncGetAttributes(&fa, kernel));
+    const long long cells = (long long)args.n_iblocks * S;
+    const dim3 grid(args.n_iblocks, S);
+    const float ms = t.best([&] { kernel<<<grid, T>>>(args); }, 4);
     const double ginter = (double)n * n / (ms * 1e-3) / 1e9;
-    printf("force %s P=%d T=%3d U=%d minB=%d regs=%3d occ=%2d blk/SM (%2d warps) grid=%5d : %8.3f ms %8.1f G int/s %5.1f %% of %.2f TF\n",
-           SA == 0 ? "pair-major" : (SA == 1 ? "scalar-acc" : "op-major  "), P, T, U, MINB, fa.numRegs, occ, occ * T / 32, grid.x * grid.y, ms, ginter,
+    printf("force %s P=%d T=%3d TJ=%3d U=%d minB=%2d regs=%3d occ=%2d blk/SM (%2d warps) cells=%5lld : %8.3f ms %8.1f G int/s %5.1f %% of %.2f TF\n",
+           ORDER == 0 ? "pair-major" : "op-major  ", P, T, TJ, U, MINB, fa.numRegs, occ, occ * T / 32, cells, ms, ginter,
            100.0 * ginter * 20.0 / 1e3 / g_peak_tflops, g_peak_tflops);
 }
 
@@ -237,189 +247,19 @@ int main(int argc, char **argv)
     CK(cudaMalloc(&partial, sizeof(float4) * n * 8));
     CK(cudaMemcpy(pos, h.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
     printf("--- force_segments_kernel, N = %d, S = 8 ---\n", n);
-    run_force<8, 128, 1, 2, 0>(pos, partial, n, t);
-    run_force<8, 128, 2, 2, 0>(pos, partial, n, t);
-    run_force<8, 128, 4, 2, 0>(pos, partial, n, t);
-    run_force<8, 128, 8, 2, 0>(pos, partial, n, t);
-    run_force<8, 256, 1, 1, 0>(pos, partial, n, t);
-    run_force<8, 256, 2, 1, 0>(pos, partial, n, t);
-    run_force<8, 256, 4, 1, 0>(pos, partial, n, t);
-    run_force<8, 256, 8, 1, 0>(pos, partial, n, t);
-    run_force<4, 256, 1, 1, 0>(pos, partial, n, t);
-    run_force<4, 256, 1, 2, 0>(pos, partial, n, t);
-    run_force<4, 256, 1, 3, 0>(pos, partial, n, t);
-    run_force<4, 256, 2, 1, 0>(pos, partial, n, t);
-    run_force<4, 256, 2, 2, 0>(pos, partial, n, t);
-    run_force<4, 256, 2, 3, 0>(pos, partial, n, t);
-    run_force<4, 256, 4, 1, 0>(pos, partial, n, t);
-    run_force<4, 256, 4, 2, 0>(pos, partial, n, t);
-    run_force<4, 256, 4, 3, 0>(pos, partial, n, t);
-    run_force<4, 256, 8, 1, 0>(pos, partial, n, t);
-    run_force<4, 256, 8, 2, 0>(pos, partial, n, t);
-    run_force<4, 256, 8, 3, 0>(pos, partial, n, t);
-    run_force<4, 128, 1, 2, 0>(pos, partial, n, t);
-    run_force<4, 128, 1, 4, 0>(pos, partial, n, t);
-    run_force<4, 128, 1, 6, 0>(pos, partial, n, t);
-    run_force<4, 128, 2, 2, 0>(pos, partial, n, t);
-    run_force<4, 128, 2, 4, 0>(pos, partial, n, t);
-    run_force<4, 128, 2, 6, 0>(pos, partial, n, t);
-    run_force<4, 128, 4, 2, 0>(pos, partial, n, t);
-    run_force<4, 128, 4, 4, 0>(pos, partial, n, t);
-    run_force<4, 128, 4, 6, 0>(pos, partial, n, t);
-    run_force<4, 128, 8, 2, 0>(pos, partial, n, t);
-    run_force<4, 128, 8, 4, 0>(pos, partial, n, t);
-    run_force<4, 128, 8, 6, 0>(pos, partial, n, t);
-    run_force<4, 64, 1, 8, 0>(pos, partial, n, t);
-    run_force<4, 64, 2, 8, 0>(pos, partial, n, t);
-    run_force<4, 64, 4, 8, 0>(pos, partial, n, t);
-    run_force<4, 64, 8, 8, 0>(pos, partial, n, t);
-    run_force<3, 256, 1, 2, 0>(pos, partial, n, t);
-    run_force<3, 256, 1, 3, 0>(pos, partial, n, t);
-    run_force<3, 256, 2, 2, 0>(pos, partial, n, t);
-    run_force<3, 256, 2, 3, 0>(pos, partial, n, t);
-    run_force<3, 256, 4, 2, 0>(pos, partial, n, t);
-    run_force<3, 256, 4, 3, 0>(pos, partial, n, t);
-    run_force<3, 256, 8, 2, 0>(pos, partial, n, t);
-    run_force<3, 256, 8, 3, 0>(pos, partial, n, t);
-    run_force<3, 128, 1, 4, 0>(pos, partial, n, t);
-    run_force<3, 128, 1, 6, 0>(pos, partial, n, t);
-    run_force<3, 128, 2, 4, 0>(pos, partial, n, t);
-    run_force<3, 128, 2, 6, 0>(pos, partial, n, t);
-    run_force<3, 128, 4, 4, 0>(pos, partial, n, t);
-    run_force<3, 128, 4, 6, 0>(pos, partial, n, t);
-    run_force<3, 128, 8, 4, 0>(pos, partial, n, t);
-    run_force<3, 128, 8, 6, 0>(pos, partial, n, t);
-    run_force<2, 256, 1, 2, 0>(pos, partial, n, t);
-    run_force<2, 256, 1, 4, 0>(pos, partial, n, t);
-    run_force<2, 256, 2, 2, 0>(pos, partial, n, t);
-    run_force<2, 256, 2, 4, 0>(pos, partial, n, t);
-    run_force<2, 256, 4, 2, 0>(pos, partial, n, t);
-    run_force<2, 256, 4, 4, 0>(pos, partial, n, t);
-    run_force<2, 256, 8, 2, 0>(pos, partial, n, t);
-    run_force<2, 256, 8, 4, 0>(pos, partial, n, t);
-    run_force<2, 128, 1, 4, 0>(pos, partial, n, t);
-    run_force<2, 128, 1, 8, 0>(pos, partial, n, t);
-    run_force<2, 128, 2, 4, 0>(pos, partial, n, t);
-    run_force<2, 128, 2, 8, 0>(pos, partial, n, t);
-    run_force<2, 128, 4, 4, 0>(pos, partial, n, t);
-    run_force<2, 128, 4, 8, 0>(pos, partial, n, t);
-    run_force<2, 128, 8, 4, 0>(pos, partial, n, t);
-    run_force<2, 128, 8, 8, 0>(pos, partial, n, t);
-    run_force<2, 64, 1, 8, 0>(pos, partial, n, t);
-    run_force<2, 64, 1, 16, 0>(pos, partial, n, t);
-    run_force<2, 64, 2, 8, 0>(pos, partial, n, t);
-    run_force<2, 64, 2, 16, 0>(pos, partial, n, t);
-    run_force<2, 64, 4, 8, 0>(pos, partial, n, t);
-    run_force<2, 64, 4, 16, 0>(pos, partial, n, t);
-    run_force<2, 64, 8, 8, 0>(pos, partial, n, t);
-    run_force<2, 64, 8, 16, 0>(pos, partial, n, t);
-    run_force<1, 256, 1, 4, 0>(pos, partial, n, t);
-    run_force<1, 256, 1, 8, 0>(pos, partial, n, t);
-    run_force<1, 256, 2, 4, 0>(pos, partial, n, t);
-    run_force<1, 256, 2, 8, 0>(pos, partial, n, t);
-    run_force<1, 256, 4, 4, 0>(pos, partial, n, t);
-    run_force<1, 256, 4, 8, 0>(pos, partial, n, t);
-    run_force<1, 256, 8, 4, 0>(pos, partial, n, t);
-    run_force<1, 256, 8, 8, 0>(pos, partial, n, t);
-    run_force<1, 128, 1, 8, 0>(pos, partial, n, t);
-    run_force<1, 128, 1, 16, 0>(pos, partial, n, t);
-    run_force<1, 128, 2, 8, 0>(pos, partial, n, t);
-    run_force<1, 128, 2, 16, 0>(pos, partial, n, t);
-    run_force<1, 128, 4, 8, 0>(pos, partial, n, t);
-    run_force<1, 128, 4, 16, 0>(pos, partial, n, t);
-    run_force<1, 128, 8, 8, 0>(pos, partial, n, t);
-    run_force<1, 128, 8, 16, 0>(pos, partial, n, t);
-    run_force<8, 128, 1, 2, 2>(pos, partial, n, t);
-    run_force<8, 128, 2, 2, 2>(pos, partial, n, t);
-    run_force<8, 128, 4, 2, 2>(pos, partial, n, t);
-    run_force<8, 128, 8, 2, 2>(pos, partial, n, t);
-    run_force<8, 256, 1, 1, 2>(pos, partial, n, t);
-    run_force<8, 256, 2, 1, 2>(pos, partial, n, t);
-    run_force<8, 256, 4, 1, 2>(pos, partial, n, t);
-    run_force<8, 256, 8, 1, 2>(pos, partial, n, t);
-    run_force<4, 256, 1, 1, 2>(pos, partial, n, t);
-    run_force<4, 256, 1, 2, 2>(pos, partial, n, t);
-    run_force<4, 256, 1, 3, 2>(pos, partial, n, t);
-    run_force<4, 256, 2, 1, 2>(pos, partial, n, t);
-    run_force<4, 256, 2, 2, 2>(pos, partial, n, t);
-    run_force<4, 256, 2, 3, 2>(pos, partial, n, t);
-    run_force<4, 256, 4, 1, 2>(pos, partial, n, t);
-    run_force<4, 256, 4, 2, 2>(pos, partial, n, t);
-    run_force<4, 256, 4, 3, 2>(pos, partial, n, t);
-    run_force<4, 256, 8, 1, 2>(pos, partial, n, t);
-    run_force<4, 256, 8, 2, 2>(pos, partial, n, t);
-    run_force<4, 256, 8, 3, 2>(pos, partial, n, t);
-    run_force<4, 128, 1, 2, 2>(pos, partial, n, t);
-    run_force<4, 128, 1, 4, 2>(pos, partial, n, t);
-    run_force<4, 128, 1, 6, 2>(pos, partial, n, t);
-    run_force<4, 128, 2, 2, 2>(pos, partial, n, t);
-    run_force<4, 128, 2, 4, 2>(pos, partial, n, t);
-    run_force<4, 128, 2, 6, 2>(pos, partial, n, t);
-    run_force<4, 128, 4, 2, 2>(pos, partial, n, t);
-    run_force<4, 128, 4, 4, 2>(pos, partial, n, t);
-    run_force<4, 128, 4, 6, 2>(pos, partial, n, t);
-    run_force<4, 128, 8, 2, 2>(pos, partial, n, t);
-    run_force<4, 128, 8, 4, 2>(pos, partial, n, t);
-    run_force<4, 128, 8, 6, 2>(pos, partial, n, t);
-    run_force<4, 64, 1, 8, 2>(pos, partial, n, t);
-    run_force<4, 64, 2, 8, 2>(pos, partial, n, t);
-    run_force<4, 64, 4, 8, 2>(pos, partial, n, t);
-    run_force<4, 64, 8, 8, 2>(pos, partial, n, t);
-    run_force<3, 256, 1, 2, 2>(pos, partial, n, t);
-    run_force<3, 256, 1, 3, 2>(pos, partial, n, t);
-    run_force<3, 256, 2, 2, 2>(pos, partial, n, t);
-    run_force<3, 256, 2, 3, 2>(pos, partial, n, t);
-    run_force<3, 256, 4, 2, 2>(pos, partial, n, t);
-    run_force<3, 256, 4, 3, 2>(pos, partial, n, t);
-    run_force<3, 256, 8, 2, 2>(pos, partial, n, t);
-    run_force<3, 256, 8, 3, 2>(pos, partial, n, t);
-    run_force<3, 128, 1, 4, 2>(pos, partial, n, t);
-    run_force<3, 128, 1, 6, 2>(pos, partial, n, t);
-    run_force<3, 128, 2, 4, 2>(pos, partial, n, t);
-    run_force<3, 128, 2, 6, 2>(pos, partial, n, t);
-    run_force<3, 128, 4, 4, 2>(pos, partial, n, t);
-    run_force<3, 128, 4, 6, 2>(pos, partial, n, t);
-    run_force<3, 128, 8, 4, 2>(pos, partial, n, t);
-    run_force<3, 128, 8, 6, 2>(pos, partial, n, t);
-    run_force<2, 256, 1, 2, 2>(pos, partial, n, t);
-    run_force<2, 256, 1, 4, 2>(pos, partial, n, t);
-    run_force<2, 256, 2, 2, 2>(pos, partial, n, t);
-    run_force<2, 256, 2, 4, 2>(pos, partial, n, t);
-    run_force<2, 256, 4, 2, 2>(pos, partial, n, t);
-    run_force<2, 256, 4, 4, 2>(pos, partial, n, t);
-    run_force<2, 256, 8, 2, 2>(pos, partial, n, t);
-    run_force<2, 256, 8, 4, 2>(pos, partial, n, t);
-    run_force<2, 128, 1, 4, 2>(pos, partial, n, t);
-    run_force<2, 128, 1, 8, 2>(pos, partial, n, t);
-    run_force<2, 128, 2, 4, 2>(pos, partial, n, t);
-    run_force<2, 128, 2, 8, 2>(pos, partial, n, t);
-    run_force<2, 128, 4, 4, 2>(pos, partial, n, t);
-    run_force<2, 128, 4, 8, 2>(pos, partial, n, t);
-    run_force<2, 128, 8, 4, 2>(pos, partial, n, t);
-    run_force<2, 128, 8, 8, 2>(pos, partial, n, t);
-    run_force<2, 64, 1, 8, 2>(pos, partial, n, t);
-    run_force<2, 64, 1, 16, 2>(pos, partial, n, t);
-    run_force<2, 64, 2, 8, 2>(pos, partial, n, t);
-    run_force<2, 64, 2, 16, 2>(pos, partial, n, t);
-    run_force<2, 64, 4, 8, 2>(pos, partial, n, t);
-    run_force<2, 64, 4, 16, 2>(pos, partial, n, t);
-    run_force<2, 64, 8, 8, 2>(pos, partial, n, t);
-    run_force<2, 64, 8, 16, 2>(pos, partial, n, t);
-    run_force<1, 256, 1, 4, 2>(pos, partial, n, t);
-    run_force<1, 256, 1, 8, 2>(pos, partial, n, t);
-    run_force<1, 256, 2, 4, 2>(pos, partial, n, t);
-    run_force<1, 256, 2, 8, 2>(pos, partial, n, t);
-    run_force<1, 256, 4, 4, 2>(pos, partial, n, t);
-    run_force<1, 256, 4, 8, 2>(pos, partial, n, t);
-    run_force<1, 256, 8, 4, 2>(pos, partial, n, t);
-    run_force<1, 256, 8, 8, 2>(pos, partial, n, t);
-    run_force<1, 128, 1, 8, 2>(pos, partial, n, t);
-    run_force<1, 128, 1, 16, 2>(pos, partial, n, t);
-    run_force<1, 128, 2, 8, 2>(pos, partial, n, t);
-    run_force<1, 128, 2, 16, 2>(pos, partial, n, t);
-    run_force<1, 128, 4, 8, 2>(pos, partial, n, t);
-    run_force<1, 128, 4, 16, 2>(pos, partial, n, t);
-    run_force<1, 128, 8, 8, 2>(pos, partial, n, t);
-    run_force<1, 128, 8, 16, 2>(pos, partial, n, t);
+    run_force<4, 256, 256, 8, 2, 0>(pos, partial, n, t);
+    run_force<4, 256, 256, 8, 1, 0>(pos, partial, n, t);
+    run_force<4, 128, 256, 8, 4, 0>(pos, partial, n, t);
+    run_force<2, 128, 256, 4, 4, 2>(pos, partial, n, t);
+    run_force<2, 128, 256, 4, 4, 0>(pos, partial, n, t);
+    run_force<2, 64, 64, 4, 8, 2>(pos, partial, n, t);
+    run_force<2, 64, 64, 8, 8, 0>(pos, partial, n, t);
+    run_force<1, 64, 64, 8, 16, 0>(pos, partial, n, t);
+    run_force<1, 64, 64, 4, 16, 0>(pos, partial, n, t);
+    run_force<1, 32, 64, 8, 32, 0>(pos, partial, n, t);
+    run_force<1, 32, 64, 4, 32, 0>(pos, partial, n, t);
+    run_force<2, 32, 64, 4, 16, 2>(pos, partial, n, t);
+    run_force<2, 32, 64, 8, 16, 0>(pos, partial, n, t);
+    run_force<8, 128, 256, 2, 2, 0>(pos, partial, n, t);
     return 0;
 }
