@@ -66,6 +66,16 @@ def read_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "_source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic(n: int, world: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the force kernel from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json); null when the workload differs from it."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return float(t["dram_bytes_per_launch"]) if world == 1 and int(t["n"]) == n else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -275,13 +285,13 @@ def run_mapc(args) -> None:
     probe_scalar, _ = pkg.fp32_peak_probe(local_rank, False)
     hbm_bytes = 80.0 * c.num_local                   # 64 B PosVelo r/w + 16 B packed mirror per body
     roofline = {
-        "bound": "fp32_fma", "kernel": "force_segments_kernel (+ integrate_kernel, <0.2 % of the step)",
+        "bound": "fp32_fma", "kernel": "force_cells_kernel (force + fused combine/integrate: the whole step is this one kernel)",
         "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
         "peak_how": f"{sms} SMs x 128 lanes x 2 flop x {sm_max_mhz:.0f} MHz ({peaks['_source']}), "
                     f"{FLOP_PER_INTERACTION:.0f} flop/interaction",
         "peak_probe_ffma2_tflops": probe_packed, "peak_probe_ffma_tflops": probe_scalar,
         "frac_of_probe": achieved_tflops / max(probe_packed, probe_scalar),
-        "kernel_ms": kernel_ms, "traffic": None,
+        "kernel_ms": kernel_ms, "traffic": ncu_traffic(n, world),
         "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9,
                 "peak_gbs": peaks.get("hbm_gbs"), "note": "negligible: the step is FMA-pipe bound"},
     }

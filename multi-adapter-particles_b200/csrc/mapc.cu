@@ -338,6 +338,8 @@ struct mapc_compute {
     cudaStream_t compute = nullptr;  // m_commandQueue (compute)
     mapc::GatedStream gcompute;      // the same stream behind the fence gate (fence.hpp)
     cudaStream_t comm = nullptr;     // all-gather stream
+    cudaStream_t compute2 = nullptr; // sharded runs: remote-segment cells, concurrent with the local ones
+    cudaEvent_t ev_step_begin = nullptr, ev_remote_done = nullptr;
     mapc_posvelo *posvelo[2] = {nullptr, nullptr};  // ping-pong sides, local shard
     float4 *packed[2] = {nullptr, nullptr};         // packed positions, all N, per side
     float4 *partial = nullptr;                      // [segments][n_local]
@@ -394,25 +396,25 @@ void resolve_timers(mapc_compute *c, bool block)
 
 // grid = (target blocks, segments of this launch): one cell per thread block
 template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE>
-mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args)
+mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream_t stream)
 {
     dim3 grid((unsigned)args.n_iblocks, (unsigned)args.segs.count, 1);
-    mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE><<<grid, T, 0, c->compute>>>(args);
+    mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE><<<grid, T, 0, stream>>>(args);
     MAPC_CUDA(cudaGetLastError());
     ++c->launches;
     return MAPC_OK;
 }
 
 template <bool FUSE>
-mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::StepArgs &args)
+mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::StepArgs &args, cudaStream_t stream)
 {
     if (args.segs.count == 0 || args.i_cnt <= 0) return MAPC_OK;
-    if (pl.pairs == 4 && pl.threads == 256) return launch_force<4, 256, 256, 8, 2, 0, FUSE>(c, args);
-    if (pl.pairs == 4 && pl.threads == 128) return launch_force<4, 128, 256, 8, 4, 0, FUSE>(c, args);
-    if (pl.pairs == 2 && pl.threads == 128) return launch_force<2, 128, 256, 4, 4, 2, FUSE>(c, args);
-    if (pl.pairs == 2 && pl.threads == 64) return launch_force<2, 64, 64, 4, 8, 2, FUSE>(c, args);
-    if (pl.pairs == 1 && pl.threads == 64) return launch_force<1, 64, 64, 8, 16, 0, FUSE>(c, args);
-    return launch_force<1, 32, 64, 8, 32, 0, FUSE>(c, args);
+    if (pl.pairs == 4 && pl.threads == 256) return launch_force<4, 256, 256, 8, 2, 0, FUSE>(c, args, stream);
+    if (pl.pairs == 4 && pl.threads == 128) return launch_force<4, 128, 256, 8, 4, 0, FUSE>(c, args, stream);
+    if (pl.pairs == 2 && pl.threads == 128) return launch_force<2, 128, 256, 4, 4, 2, FUSE>(c, args, stream);
+    if (pl.pairs == 2 && pl.threads == 64) return launch_force<2, 64, 64, 4, 8, 2, FUSE>(c, args, stream);
+    if (pl.pairs == 1 && pl.threads == 64) return launch_force<1, 64, 64, 8, 16, 0, FUSE>(c, args, stream);
+    return launch_force<1, 32, 64, 8, 32, 0, FUSE>(c, args, stream);
 }
 
 // targets of this shard that a Simulate(n_active) updates, as a count from i_first
@@ -474,6 +476,9 @@ mapc_status create_common(mapc_compute **out, uint32_t n, int device, int rank, 
         c->gcompute.stream = c->compute;
         c->gcompute.device = device;
         MAPC_CUDA(cudaStreamCreateWithFlags(&c->comm, cudaStreamNonBlocking));
+        MAPC_CUDA(cudaStreamCreateWithFlags(&c->compute2, cudaStreamNonBlocking));
+        MAPC_CUDA(cudaEventCreateWithFlags(&c->ev_step_begin, cudaEventDisableTiming));
+        MAPC_CUDA(cudaEventCreateWithFlags(&c->ev_remote_done, cudaEventDisableTiming));
         for (int s = 0; s < 2; ++s) {
             MAPC_CUDA(cudaMalloc(&c->posvelo[s], (size_t)c->n_local * sizeof(mapc_posvelo)));
             MAPC_CUDA(cudaMalloc(&c->packed[s], (size_t)n * sizeof(float4)));
@@ -669,7 +674,11 @@ mapc_status mapc_compute_destroy(mapc_compute *c)
         if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]);
         if (c->t_end[k]) cudaEventDestroy(c->t_end[k]);
     }
+    if (c->compute2) cudaStreamSynchronize(c->compute2);
+    if (c->ev_step_begin) cudaEventDestroy(c->ev_step_begin);
+    if (c->ev_remote_done) cudaEventDestroy(c->ev_remote_done);
     if (c->compute) cudaStreamDestroy(c->compute);
+    if (c->compute2) cudaStreamDestroy(c->compute2);
     if (c->comm) cudaStreamDestroy(c->comm);
     mapc_fence_destroy(c->fence);
     delete c;
@@ -792,12 +801,22 @@ static mapc_status enqueue_step(mapc_compute *c, uint32_t b, int n_targets, int 
                                       (j0 >= (int)c->i_first && j1 <= (int)(c->i_first + c->n_local));
                 (is_local ? local : remote).ids[(is_local ? local : remote).count++] = s;
             }
+            // Local cells go on the compute stream at once; the remote cells go on a second stream that
+            // waits for the all-gather, so both grids are resident together and the block scheduler
+            // balances them (a lone local launch of few, long cells would leave most SMs idle).  The
+            // arrival counters make the fused combine+integrate independent of which grid finishes last.
+            if (remote.count > 0) MAPC_CUDA(cudaEventRecord(c->ev_step_begin, c->compute));
             args.segs = local;
-            MAPC_TRY(fuse ? launch_force_shape<true>(c, pl, args) : launch_force_shape<false>(c, pl, args));
+            MAPC_TRY(fuse ? launch_force_shape<true>(c, pl, args, c->compute)
+                          : launch_force_shape<false>(c, pl, args, c->compute));
             if (remote.count > 0) {
-                MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_gathered[r], 0));
+                MAPC_CUDA(cudaStreamWaitEvent(c->compute2, c->ev_step_begin, 0));
+                MAPC_CUDA(cudaStreamWaitEvent(c->compute2, c->ev_gathered[r], 0));
                 args.segs = remote;
-                MAPC_TRY(fuse ? launch_force_shape<true>(c, pl, args) : launch_force_shape<false>(c, pl, args));
+                MAPC_TRY(fuse ? launch_force_shape<true>(c, pl, args, c->compute2)
+                              : launch_force_shape<false>(c, pl, args, c->compute2));
+                MAPC_CUDA(cudaEventRecord(c->ev_remote_done, c->compute2));
+                MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_remote_done, 0));
             }
             if (!fuse) {
                 mapc::integrate_kernel<<<(n_targets + 255) / 256, 256, 0, c->compute>>>(
