@@ -218,6 +218,8 @@ def run_mapc(args) -> None:
 
     c = pkg.Compute(n, local_rank, rank=rank, world=world, nccl_id=nccl_id)
     c.Upload(particles)
+    if world > 1 and args.exchange == "peer":
+        pkg.dist.enable_peer_exchange(c, dev)
     sh = c.GetSharedHandles()
     stream = torch.cuda.ExternalStream(sh.compute_stream, device=dev)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -261,11 +263,17 @@ def run_mapc(args) -> None:
     host_out = torch.empty((c.num_local, 8), dtype=torch.float32, pin_memory=True)
     out_view = host_out.numpy().view(pkg.POSVELO_DTYPE).reshape(-1)
     e2e_steps = max(1, min(args.steps, 10))
+    peer = world > 1 and args.exchange == "peer"
+
     for _ in range(2):
+        if peer:
+            dist.barrier()                           # a peer may still be reading this rank's buffers
         c.Upload(host_in.numpy()); c.Simulate(n, 0, DT, DAMPING); c.Download(out=out_view)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
+        if peer:
+            dist.barrier()
         c.Upload(host_in.numpy())                    # H2D of all N bodies (pinned host memory)
         c.Simulate(n, 0, DT, DAMPING)
         c.Download(out=out_view)                     # D2H of this rank's shard; blocks
@@ -310,7 +318,7 @@ def run_mapc(args) -> None:
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"allpairs uniform sphere N={n} seed={SEED} dt={DT} damping={DAMPING}",
-                       "n": n, "n_per_gpu": c.num_local, "plan": c.Plan(), "parallelism": f"i-shard x{world}",
+                       "n": n, "n_per_gpu": c.num_local, "plan": c.Plan(), "parallelism": f"i-shard x{world}" + (f" ({args.exchange} exchange)" if world > 1 else ""),
                        "l2": "no flush (latency run)" if args.no_l2_flush else
                              "256 MiB memset between timed steps (inside the bracket)"},
             "step_us": {"min": float(step_ms.min() * 1e3), "median": float(np.median(step_ms) * 1e3),
@@ -339,6 +347,8 @@ def main() -> None:
     ap.add_argument("--impl", choices=["mapc", "reference"], default="mapc")
     ap.add_argument("--n", type=int, default=None, help="override the number of bodies")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
+    ap.add_argument("--exchange", choices=["nccl", "peer"], default="nccl",
+                    help="multi-GPU position exchange: NCCL all-gather, or direct peer-memory reads in the force kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true",
                     help="latency runs (N = 10,000, config 2): no 256 MiB memset between steps")

@@ -44,6 +44,7 @@ extern "C" {
 #define MAPC_MAX_NUM_PARTICLES      (4 * 1024 * 1024)  /* Particles/defines.h:45               */
 #define MAPC_MAX_SEGMENTS           64
 #define MAPC_NCCL_UNIQUE_ID_BYTES   128
+#define MAPC_IPC_BLOB_BYTES         256
 
 /* struct PosVelo { float4 pos; float4 velo; }  Particles/ParticleShared.hlsl:12-16.
  * pos[3] carries length(accel) after a step (nBodyGravityCS.hlsl:107); velo[3] is 0 (the
@@ -115,6 +116,18 @@ MAPC_API mapc_status mapc_nccl_unique_id(void *out_id);
 MAPC_API mapc_status mapc_compute_create_sharded(mapc_compute **out, uint32_t num_particles,
                                                  int device, int rank, int world,
                                                  const void *nccl_unique_id);
+
+/* Collective-free exchange (optional, after create_sharded + upload): every rank exports the IPC
+ * handles of its packed position buffers and step flag (MAPC_IPC_BLOB_BYTES bytes), the caller
+ * gathers the `world` blobs in rank order, and every rank attaches them.  From then on a step reads
+ * the other ranks' segments straight from their memory over NVLink inside the force kernel, gated by
+ * per-rank step flags, instead of all-gathering positions with NCCL.  Same canonical order, same
+ * bits.  The caller must barrier the ranks between upload/attach and the first Simulate.  Once
+ * attached, all-pairs steps whose segments do not align with the shards (n_active != N, or a segment
+ * straddling two shards) are refused with MAPC_ERR_UNSUPPORTED.  (Closest reference idea: both
+ * adapters addressing one shared heap, Compute.cpp:165-199.) */
+MAPC_API mapc_status mapc_compute_ipc_export(mapc_compute *c, void *out_blob);
+MAPC_API mapc_status mapc_compute_ipc_attach(mapc_compute *c, const void *blobs_all_ranks, int world);
 
 /* Compute::~Compute, Compute.cpp:102-123: drains the device, frees everything the handle owns */
 MAPC_API mapc_status mapc_compute_destroy(mapc_compute *c);

@@ -38,6 +38,7 @@ DEFAULT_DAMPING = 1.0
 MIN_NUM_PARTICLES = 256 * 1024
 MAX_NUM_PARTICLES = 4 * 1024 * 1024
 NCCL_UNIQUE_ID_BYTES = 128
+IPC_BLOB_BYTES = 256
 
 FORCE_ALLPAIRS = 0
 FORCE_WELL = 1
@@ -66,6 +67,7 @@ EXPORTED_SYMBOLS = (
     "mapc_compute_step_times", "mapc_compute_flush",
     "mapc_consumer_create", "mapc_consumer_destroy", "mapc_consumer_draw", "mapc_consumer_latest",
     "mapc_consumer_wait_for_gpu", "mapc_consumer_counters",
+    "mapc_compute_ipc_export", "mapc_compute_ipc_attach",
 )
 
 
@@ -155,6 +157,8 @@ def load() -> ctypes.CDLL:
         "mapc_consumer_latest": (c_int, [c_void_p, P(P(c_float)), P(c_uint64), P(c_uint32)]),
         "mapc_consumer_wait_for_gpu": (c_int, [c_void_p]),
         "mapc_consumer_counters": (c_int, [c_void_p, P(c_uint64)]),
+        "mapc_compute_ipc_export": (c_int, [c_void_p, c_void_p]),
+        "mapc_compute_ipc_attach": (c_int, [c_void_p, c_void_p, c_int]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -341,6 +345,17 @@ class Compute:
         _check(self._lib.mapc_compute_plan(self._h, n_active, byref(p), byref(t), byref(b), byref(s)))
         return {"pairs_per_thread": p.value, "threads_per_block": t.value, "blocks": b.value,
                 "segments": s.value}
+
+    def IpcExport(self) -> bytes:
+        """This rank's blob for the collective-free exchange (mapc_compute_ipc_export)."""
+        buf = ctypes.create_string_buffer(IPC_BLOB_BYTES)
+        _check(self._lib.mapc_compute_ipc_export(self._h, buf))
+        return buf.raw
+
+    def IpcAttach(self, blobs) -> None:
+        """Attach the blobs of all ranks (rank order): steps then read peers' memory instead of all-gathering."""
+        data = b"".join(blobs)
+        _check(self._lib.mapc_compute_ipc_attach(self._h, data, len(blobs)))
 
     def StepTimes(self, capacity: int = 4096) -> np.ndarray:
         """Raw "simulate ms" samples resolved since the previous call (oldest first)."""

@@ -353,6 +353,12 @@ struct mapc_compute {
     uint32_t buffer_index = 0;              // m_bufferIndex
 
     ncclComm_t nccl = nullptr;
+    // collective-free exchange (mapc_compute_ipc_attach)
+    bool peer_mode = false;
+    unsigned long long *flag = nullptr;          // own step flag (device memory, IPC-exported)
+    float4 *peer_packed[16][2] = {};             // [rank][side]: own pointers for rank == c->rank
+    unsigned long long *peer_flag[16] = {};
+    unsigned long long step_id = 0;              // steps issued since attach (same on every rank)
     cudaEvent_t ev_integrated = nullptr;
     cudaEvent_t ev_gathered[2] = {nullptr, nullptr};
     bool gather_pending[2] = {false, false};
@@ -395,26 +401,26 @@ void resolve_timers(mapc_compute *c, bool block)
 }
 
 // grid = (target blocks, segments of this launch): one cell per thread block
-template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE>
+template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER>
 mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream_t stream)
 {
     dim3 grid((unsigned)args.n_iblocks, (unsigned)args.segs.count, 1);
-    mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE><<<grid, T, 0, stream>>>(args);
+    mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER><<<grid, T, 0, stream>>>(args);
     MAPC_CUDA(cudaGetLastError());
     ++c->launches;
     return MAPC_OK;
 }
 
-template <bool FUSE>
+template <bool FUSE, bool PEER = false>
 mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::StepArgs &args, cudaStream_t stream)
 {
     if (args.segs.count == 0 || args.i_cnt <= 0) return MAPC_OK;
-    if (pl.pairs == 4 && pl.threads == 256) return launch_force<4, 256, 256, 8, 2, 0, FUSE>(c, args, stream);
-    if (pl.pairs == 4 && pl.threads == 128) return launch_force<4, 128, 256, 8, 4, 0, FUSE>(c, args, stream);
-    if (pl.pairs == 2 && pl.threads == 128) return launch_force<2, 128, 256, 4, 4, 2, FUSE>(c, args, stream);
-    if (pl.pairs == 2 && pl.threads == 64) return launch_force<2, 64, 64, 4, 8, 2, FUSE>(c, args, stream);
-    if (pl.pairs == 1 && pl.threads == 64) return launch_force<1, 64, 64, 8, 16, 0, FUSE>(c, args, stream);
-    return launch_force<1, 32, 64, 8, 32, 0, FUSE>(c, args, stream);
+    if (pl.pairs == 4 && pl.threads == 256) return launch_force<4, 256, 256, 8, 2, 0, FUSE, PEER>(c, args, stream);
+    if (pl.pairs == 4 && pl.threads == 128) return launch_force<4, 128, 256, 8, 4, 0, FUSE, PEER>(c, args, stream);
+    if (pl.pairs == 2 && pl.threads == 128) return launch_force<2, 128, 256, 4, 4, 2, FUSE, PEER>(c, args, stream);
+    if (pl.pairs == 2 && pl.threads == 64) return launch_force<2, 64, 64, 4, 8, 2, FUSE, PEER>(c, args, stream);
+    if (pl.pairs == 1 && pl.threads == 64) return launch_force<1, 64, 64, 8, 16, 0, FUSE, PEER>(c, args, stream);
+    return launch_force<1, 32, 64, 8, 32, 0, FUSE, PEER>(c, args, stream);
 }
 
 // targets of this shard that a Simulate(n_active) updates, as a count from i_first
@@ -662,6 +668,14 @@ mapc_status mapc_compute_destroy(mapc_compute *c)
     if (c->compute) cudaStreamSynchronize(c->compute);
     if (c->comm) cudaStreamSynchronize(c->comm);
     if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
+    if (c->peer_mode)
+        for (int p = 0; p < c->world && p < 16; ++p)
+            if (p != c->rank) {
+                for (int sd = 0; sd < 2; ++sd)
+                    if (c->peer_packed[p][sd]) cudaIpcCloseMemHandle(c->peer_packed[p][sd]);
+                if (c->peer_flag[p]) cudaIpcCloseMemHandle(c->peer_flag[p]);
+            }
+    if (c->flag) cudaFree(c->flag);
     for (int s = 0; s < 2; ++s) {
         if (c->posvelo[s]) cudaFree(c->posvelo[s]);
         if (c->packed[s]) cudaFree(c->packed[s]);
@@ -756,6 +770,7 @@ static mapc_status enqueue_step(mapc_compute *c, uint32_t b, int n_targets, int 
                                 float damping, mapc_force_mode mode)
 {
     const uint32_t r = 1u - b;  // read side (reads 1-b, writes b)
+    bool use_peer = false;
     resolve_timers(c, false);
     const int slot = (int)(c->t_next % mapc_compute::kTimerSlots);
     if (c->t_pending[slot]) resolve_timers(c, true);
@@ -794,13 +809,23 @@ static mapc_status enqueue_step(mapc_compute *c, uint32_t b, int n_targets, int 
             args.dt = delta_time;
             args.damping = damping;
             mapc::SegList local{0, {}}, remote{0, {}};
+            int owner[MAPC_MAX_SEGMENTS];
+            bool peer = c->peer_mode && fuse && n_sources == (int)c->n && env_int("MAPC_PEER", 1) != 0;
             for (int s = 0; s < pl.segments; ++s) {
                 int j0, j1;
                 mapc::segment_range(n_sources, pl.segments, s, j0, j1);
-                const bool is_local = c->world == 1 || !c->gather_pending[r] ||
-                                      (j0 >= (int)c->i_first && j1 <= (int)(c->i_first + c->n_local));
+                const bool inside = j0 >= (int)c->i_first && j1 <= (int)(c->i_first + c->n_local);
+                owner[s] = j1 > j0 ? j0 / (int)c->n_local : c->rank;
+                if (j1 > j0 && (j1 - 1) / (int)c->n_local != owner[s]) peer = false;  // straddles two shards
+                const bool is_local = c->world == 1 || inside || (!c->peer_mode && !c->gather_pending[r]);
                 (is_local ? local : remote).ids[(is_local ? local : remote).count++] = s;
             }
+            if (c->peer_mode && !peer && remote.count > 0 && !c->gather_pending[r]) {
+                // exchange falls back to NCCL for this step, but the read side was never gathered
+                return fail(MAPC_ERR_UNSUPPORTED, "peer exchange attached but this step's segments do not align "
+                            "with the shards (n_active %d, N %u, S %d, world %d)", n_sources, c->n, pl.segments, c->world);
+            }
+            use_peer = peer && c->world > 1;
             // Local cells go on the compute stream at once; the remote cells go on a second stream that
             // waits for the all-gather, so both grids are resident together and the block scheduler
             // balances them (a lone local launch of few, long cells would leave most SMs idle).  The
@@ -811,10 +836,21 @@ static mapc_status enqueue_step(mapc_compute *c, uint32_t b, int n_targets, int 
                           : launch_force_shape<false>(c, pl, args, c->compute));
             if (remote.count > 0) {
                 MAPC_CUDA(cudaStreamWaitEvent(c->compute2, c->ev_step_begin, 0));
-                MAPC_CUDA(cudaStreamWaitEvent(c->compute2, c->ev_gathered[r], 0));
                 args.segs = remote;
-                MAPC_TRY(fuse ? launch_force_shape<true>(c, pl, args, c->compute2)
-                              : launch_force_shape<false>(c, pl, args, c->compute2));
+                if (use_peer) {
+                    // no collective: remote cells read the owners' memory, gated by the owners' step flags
+                    for (int k = 0; k < remote.count; ++k) {
+                        const int o = owner[remote.ids[k]];
+                        args.seg_src[k] = c->peer_packed[o][r];
+                        args.seg_flag[k] = c->peer_flag[o];
+                    }
+                    args.flag_expect = c->step_id;   // owners must have completed step_id steps
+                    MAPC_TRY((launch_force_shape<true, true>(c, pl, args, c->compute2)));
+                } else {
+                    MAPC_CUDA(cudaStreamWaitEvent(c->compute2, c->ev_gathered[r], 0));
+                    MAPC_TRY(fuse ? launch_force_shape<true>(c, pl, args, c->compute2)
+                                  : launch_force_shape<false>(c, pl, args, c->compute2));
+                }
                 MAPC_CUDA(cudaEventRecord(c->ev_remote_done, c->compute2));
                 MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_remote_done, 0));
             }
@@ -831,7 +867,16 @@ static mapc_status enqueue_step(mapc_compute *c, uint32_t b, int n_targets, int 
     c->t_pending[slot] = true;
     ++c->t_next;
 
-    if (c->world > 1) {
+    if (c->world > 1 && c->peer_mode) {
+        // Publish: this rank's positions of step step_id+1 are in place (and it has finished reading
+        // everybody's previous ones).  A well-mode or zero-target step publishes too, so peers never wait.
+        c->step_id++;
+        MAPC_TRY(load_stream_memops());
+        const CUresult wr = g_write64((CUstream)c->compute, (CUdeviceptr)(uintptr_t)c->flag, c->step_id,
+                                      CU_STREAM_WRITE_VALUE_DEFAULT);
+        if (wr != CUDA_SUCCESS) return fail(MAPC_ERR_CUDA, "cuStreamWriteValue64(step flag) failed: %d", (int)wr);
+    }
+    if (c->world > 1 && !use_peer && !c->peer_mode) {
         // exchange step: every rank contributes its slice of the freshly written packed positions
         if (c->gather_pending[r]) MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_gathered[r], 0));
         MAPC_CUDA(cudaEventRecord(c->ev_integrated, c->compute));
@@ -924,6 +969,63 @@ mapc_status mapc_compute_gpu_times(mapc_compute *c, float *ms_average, float *ms
     resolve_timers(c, false);
     if (ms_average) *ms_average = c->ms_average;
     if (ms_last) *ms_last = c->ms_last;
+    return MAPC_OK;
+}
+
+namespace {
+struct IpcBlob {
+    cudaIpcMemHandle_t packed[2];
+    cudaIpcMemHandle_t flag;
+    uint32_t n, rank;
+};
+static_assert(sizeof(IpcBlob) <= MAPC_IPC_BLOB_BYTES, "IPC blob size");
+}  // namespace
+
+mapc_status mapc_compute_ipc_export(mapc_compute *c, void *out_blob)
+{
+    if (!c || !out_blob) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (c->world < 2) return fail(MAPC_ERR_INVALID_ARGUMENT, "peer exchange needs a sharded handle");
+    DeviceGuard g(c->device);
+    if (!c->flag) {
+        MAPC_CUDA(cudaMalloc(&c->flag, 256));
+        MAPC_CUDA(cudaMemset(c->flag, 0, 256));
+    }
+    IpcBlob b;
+    memset(&b, 0, sizeof(b));
+    for (int sd = 0; sd < 2; ++sd) MAPC_CUDA(cudaIpcGetMemHandle(&b.packed[sd], c->packed[sd]));
+    MAPC_CUDA(cudaIpcGetMemHandle(&b.flag, c->flag));
+    b.n = c->n;
+    b.rank = (uint32_t)c->rank;
+    memset(out_blob, 0, MAPC_IPC_BLOB_BYTES);
+    memcpy(out_blob, &b, sizeof(b));
+    return MAPC_OK;
+}
+
+mapc_status mapc_compute_ipc_attach(mapc_compute *c, const void *blobs_all_ranks, int world)
+{
+    if (!c || !blobs_all_ranks) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (world != c->world || world > 16) return fail(MAPC_ERR_INVALID_ARGUMENT, "world %d does not match the handle (%d, max 16)", world, c->world);
+    if (!c->flag) return fail(MAPC_ERR_INVALID_ARGUMENT, "call mapc_compute_ipc_export first");
+    if (c->peer_mode) return fail(MAPC_ERR_INVALID_ARGUMENT, "already attached");
+    MAPC_TRY(mapc_compute_wait_for_gpu(c));
+    DeviceGuard g(c->device);
+    for (int p = 0; p < world; ++p) {
+        IpcBlob b;
+        memcpy(&b, (const char *)blobs_all_ranks + (size_t)p * MAPC_IPC_BLOB_BYTES, sizeof(b));
+        if (b.n != c->n || (int)b.rank != p) return fail(MAPC_ERR_INVALID_ARGUMENT, "blob %d is from rank %u with N=%u", p, b.rank, b.n);
+        if (p == c->rank) {
+            c->peer_packed[p][0] = c->packed[0];
+            c->peer_packed[p][1] = c->packed[1];
+            c->peer_flag[p] = c->flag;
+            continue;
+        }
+        for (int sd = 0; sd < 2; ++sd)
+            MAPC_CUDA(cudaIpcOpenMemHandle((void **)&c->peer_packed[p][sd], b.packed[sd], cudaIpcMemLazyEnablePeerAccess));
+        MAPC_CUDA(cudaIpcOpenMemHandle((void **)&c->peer_flag[p], b.flag, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->peer_mode = true;
+    c->step_id = 0;
+    c->gather_pending[0] = c->gather_pending[1] = false;
     return MAPC_OK;
 }
 

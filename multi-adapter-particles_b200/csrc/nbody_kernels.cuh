@@ -176,7 +176,20 @@ struct StepArgs {
     mapc_posvelo *out;         // PosVelo write side
     float4 *pos_next;          // packed positions of the write side (global indexing)
     float dt, damping;
+    // PEER (collective-free multi-GPU): per segment of this launch (indexed like segs.ids) the packed
+    // array of the rank that owns those sources -- a peer-mapped pointer read over NVLink -- and that
+    // rank's step flag, which must reach flag_expect before its positions of this step may be read
+    const float4 *seg_src[MAPC_MAX_SEGMENTS];
+    const unsigned long long *seg_flag[MAPC_MAX_SEGMENTS];
+    unsigned long long flag_expect;
 };
+
+__device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // Force kernel.  Work is cut into cells = (target block of T*2P bodies) x (canonical segment); one
 // thread block evaluates one cell: blockIdx.x = target block, blockIdx.y = index into args.segs.  (A
@@ -188,7 +201,10 @@ struct StepArgs {
 // -- so only the globally last tile is ever ragged.
 // U = unroll of the source loop, MINB = resident blocks per SM asked of ptxas.  None of P, T, TJ, U,
 // MINB or ORDER changes a rounding: each target's chain is the same ops in ascending j.
-template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE>
+// PEER: the cell's sources are read straight from the owning GPU's memory (no all-gather): the block
+// first waits until the owner's step flag says its positions of this step are published.  Waiting
+// cannot deadlock: a peer's step k-1 never depends on this GPU's step k.
+template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER = false>
 __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_constant__ StepArgs a)
 {
     constexpr int kLoads = TJ / T;  // staging loads per thread per stage
@@ -198,6 +214,15 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
 
     const int tid = threadIdx.x;
     const float4 *__restrict__ pos = a.pos;
+    const float4 *__restrict__ src = PEER ? a.seg_src[blockIdx.y] : a.pos;   // where this cell's sources live
+    if (PEER) {
+        const unsigned long long *flag = a.seg_flag[blockIdx.y];
+        if (flag != nullptr) {
+            if (tid == 0)
+                while (load_acquire_sys(flag) < a.flag_expect) __nanosleep(200);
+            __syncthreads();
+        }
+    }
     {
         const int ib = blockIdx.x;
         const int seg = a.segs.ids[blockIdx.y];
@@ -228,7 +253,7 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
 #pragma unroll
             for (int l = 0; l < kLoads; ++l) {
                 const int j = j0 + l * T + tid;
-                stage[l] = j < j1 ? pos[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                stage[l] = j < j1 ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int l = 0; l < kLoads; ++l) tile[0][l * T + tid] = stage[l];
@@ -243,7 +268,7 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
 #pragma unroll
                 for (int l = 0; l < kLoads; ++l) {
                     const int j = jt + TJ + l * T + tid;
-                    stage[l] = j < j1 ? pos[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    stage[l] = j < j1 ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             const int cnt = (j1 - jt) < TJ ? (j1 - jt) : TJ;

@@ -65,3 +65,22 @@ def max_over_ranks(x: float, device=None) -> float:
     t = torch.tensor([x], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def all_gather_bytes(data: bytes, device=None):
+    """Every rank contributes `data` (same length everywhere); returns the list in rank order."""
+    import torch
+    import torch.distributed as dist
+    mine = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(device) if device is not None else \
+        torch.frombuffer(bytearray(data), dtype=torch.uint8).clone()
+    outs = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, mine)
+    return [bytes(o.cpu().numpy().tobytes()) for o in outs]
+
+
+def enable_peer_exchange(compute, device=None) -> None:
+    """Switch a sharded Compute to the collective-free exchange: export, all-gather the blobs, attach,
+    and barrier so nobody starts stepping before every rank has uploaded and attached."""
+    import torch.distributed as dist
+    compute.IpcAttach(all_gather_bytes(compute.IpcExport(), device))
+    dist.barrier()

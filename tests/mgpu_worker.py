@@ -21,8 +21,9 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, nargs="+", default=[8192, 10_000, 32_768])
+    ap.add_argument("--n", type=int, nargs="+", default=[8192, 10_000, 32_768, 262_144])
     ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--exchange", choices=["nccl", "peer", "both"], default="both")
     args = ap.parse_args()
 
     import torch
@@ -33,37 +34,48 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     pkg = importlib.import_module("multi-adapter-particles_b200")
     pkg.load()
-    nccl_id = pkg.dist.broadcast_bytes(pkg.nccl_unique_id() if rank == 0 else None, pkg.NCCL_UNIQUE_ID_BYTES, 0, dev)
-
     ok = True
+    modes = ["nccl", "peer"] if args.exchange == "both" else [args.exchange]
     for n in args.n:
         if n % world:
             continue
         radius = 2000.0 * (n / 10_000.0) ** (1.0 / 3.0)
         p = pkg.ic.uniform_sphere(n, radius, seed=n, speed=1.0)
-        with pkg.Compute(n, local_rank, rank=rank, world=world, nccl_id=nccl_id if n == args.n[0] else
-                         pkg.dist.broadcast_bytes(pkg.nccl_unique_id() if rank == 0 else None,
-                                                  pkg.NCCL_UNIQUE_ID_BYTES, 0, dev)) as c:
-            c.Upload(p)
-            for _ in range(args.steps):
-                c.Simulate(n, 0)
-            c.WaitForGpu()
-            mine = c.Download()
-            first, count = c.first_particle, c.num_local
         with pkg.Compute(n, local_rank) as s:
             s.Upload(p)
             for _ in range(args.steps):
                 s.Simulate(n, 0)
             s.WaitForGpu()
             full = s.Download()
-        same = mine.tobytes() == full[first:first + count].tobytes()
         digest = hashlib.sha256(full.tobytes()).hexdigest()[:16]
-        flag = torch.tensor([1 if same else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if rank == 0:
-            print(f"n={n} world={world} steps={args.steps} bit-identical={bool(flag.item())} sha256[:16]={digest}",
-                  flush=True)
-        ok = ok and bool(flag.item())
+        for mode in modes:
+            first, count = pkg.dist.shard_range(n, rank, world)
+            S = pkg.plan_segments(n)
+            aligned = all((a // count) == ((b - 1) // count) for a, b in
+                          (pkg.dist.segment_range(n, S, k) for k in range(S)) if b > a)
+            if mode == "peer" and not aligned:
+                if rank == 0:
+                    print(f"n={n} world={world} exchange=peer skipped (segments straddle shards)", flush=True)
+                continue
+            nid = pkg.dist.broadcast_bytes(pkg.nccl_unique_id() if rank == 0 else None, pkg.NCCL_UNIQUE_ID_BYTES, 0, dev)
+            with pkg.Compute(n, local_rank, rank=rank, world=world, nccl_id=nid) as c:
+                c.Upload(p)
+                if mode == "peer":
+                    pkg.dist.enable_peer_exchange(c, dev)
+                else:
+                    dist.barrier()
+                for _ in range(args.steps):
+                    c.Simulate(n, 0)
+                c.WaitForGpu()
+                mine = c.Download()
+                dist.barrier()          # nobody tears its buffers down while a peer may still read them
+            same = mine.tobytes() == full[first:first + count].tobytes()
+            flag = torch.tensor([1 if same else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print(f"n={n} world={world} steps={args.steps} exchange={mode} bit-identical={bool(flag.item())} "
+                      f"sha256[:16]={digest}", flush=True)
+            ok = ok and bool(flag.item())
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
