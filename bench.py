@@ -345,7 +345,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["mapc", "reference"], default="mapc")
-    ap.add_argument("--n", type=int, default=None, help="override the number of bodies")
+    ap.add_argument("--bodies", "--n", dest="n", type=int, default=None,
+                    help="override the number of bodies (use --bodies under torchrun: its parser rejects --n as ambiguous)")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
     ap.add_argument("--exchange", choices=["nccl", "peer"], default="nccl",
                     help="multi-GPU position exchange: NCCL all-gather, or direct peer-memory reads in the force kernel")

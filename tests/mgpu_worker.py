@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, nargs="+", default=[8192, 10_000, 32_768, 262_144])
+    ap.add_argument("--bodies", dest="n", type=int, nargs="+", default=[8192, 10_000, 32_768, 262_144])
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--exchange", choices=["nccl", "peer", "both"], default="both")
     args = ap.parse_args()
