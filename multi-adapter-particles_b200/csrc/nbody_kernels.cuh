@@ -67,7 +67,7 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 // 2 when all three differ, tools/ubench), while scalar FFMA runs 3-operand at full rate -- so the
 // accumulations are issued as six scalar FFMAs on the halves of the same registers.  Same IEEE
 // fma per lane either way: the bits do not change.
-template <bool SCALAR_ACC>
+template <int SCALAR_ACC>
 __device__ __forceinline__ void pair_interaction(const float4 b, const float2 nxi, const float2 nyi,
                                                  const float2 nzi, float2 &ax, float2 &ay, float2 &az)
 {
@@ -83,7 +83,16 @@ __device__ __forceinline__ void pair_interaction(const float4 b, const float2 nx
     const float2 inv2 = __fmul2_rn(inv, inv);
     const float2 inv3 = __fmul2_rn(inv2, inv);
     const float2 s = __fmul2_rn(inv3, make_float2(MAPC_PARTICLE_MASS, MAPC_PARTICLE_MASS));
-    if (SCALAR_ACC) {
+    if (SCALAR_ACC == 2) {
+        // crossed halves: the accumulator pair holds {target b, target a}, so each scalar FFMA reads two
+        // registers of one parity and one of the other (no three-way register-bank conflict)
+        ax.y = __fmaf_rn(dx.x, s.x, ax.y);
+        ax.x = __fmaf_rn(dx.y, s.y, ax.x);
+        ay.y = __fmaf_rn(dy.x, s.x, ay.y);
+        ay.x = __fmaf_rn(dy.y, s.y, ay.x);
+        az.y = __fmaf_rn(dz.x, s.x, az.y);
+        az.x = __fmaf_rn(dz.y, s.y, az.x);
+    } else if (SCALAR_ACC == 1) {
         ax.x = __fmaf_rn(dx.x, s.x, ax.x);
         ax.y = __fmaf_rn(dx.y, s.y, ax.y);
         ay.x = __fmaf_rn(dy.x, s.x, ay.x);
@@ -283,7 +292,7 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                     } else {
 #pragma unroll
                         for (int p = 0; p < P; ++p)
-                            pair_interaction<false>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+                            pair_interaction<(ORDER == 3 ? 2 : 0)>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
                     }
                 }
             }
@@ -293,7 +302,7 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                 const float4 b = tile[buf][j];
 #pragma unroll
                 for (int p = 0; p < P; ++p)
-                    pair_interaction<false>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+                    pair_interaction<(ORDER == 3 ? 2 : 0)>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
             }
             if (has_next) {
 #pragma unroll
@@ -307,8 +316,13 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
         for (int p = 0; p < P; ++p) {
             const int ia = i_block + (2 * p) * T + tid;
             const int ib2 = i_block + (2 * p + 1) * T + tid;
-            if (ia < a.i_cnt) out[ia] = make_float4(ax[p].x, ay[p].x, az[p].x, 0.f);
-            if (ib2 < a.i_cnt) out[ib2] = make_float4(ax[p].y, ay[p].y, az[p].y, 0.f);
+            if (ORDER == 3) {  // crossed accumulators: .y belongs to target a, .x to target b
+                if (ia < a.i_cnt) out[ia] = make_float4(ax[p].y, ay[p].y, az[p].y, 0.f);
+                if (ib2 < a.i_cnt) out[ib2] = make_float4(ax[p].x, ay[p].x, az[p].x, 0.f);
+            } else {
+                if (ia < a.i_cnt) out[ia] = make_float4(ax[p].x, ay[p].x, az[p].x, 0.f);
+                if (ib2 < a.i_cnt) out[ib2] = make_float4(ax[p].y, ay[p].y, az[p].y, 0.f);
+            }
         }
 
         if (FUSE) {

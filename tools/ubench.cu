@@ -82,12 +82,15 @@ __global__ void __launch_bounds__(256) mb_ffma(float2 *out, const float2 *__rest
             if (PATTERN == 0) {
                 acc[k].x = __fmaf_rn(acc[k].x, s.x, s.y);
                 acc[k].y = __fmaf_rn(acc[k].y, s.x, s.y);
+            } else if (PATTERN == 3) {
+                acc[k].y = __fmaf_rn(x[k].x, y[k].x, acc[k].y);
+                acc[k].x = __fmaf_rn(x[k].y, y[k].y, acc[k].x);
             } else {
                 acc[k].x = __fmaf_rn(x[k].x, y[k].x, acc[k].x);
                 acc[k].y = __fmaf_rn(x[k].y, y[k].y, acc[k].y);
             }
         }
-        if (PATTERN == 2) {  // keep x, y alive as packed pairs so their halves sit in aligned registers
+        if (PATTERN >= 2) {  // keep x, y alive as packed pairs so their halves sit in aligned registers
 #pragma unroll
             for (int k = 0; k < kChains; ++k) x[k] = __fadd2_rn(x[k], y[k]);
         }
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(256) mb_mufu(float *out, const float2 *__restr
             if (MIX) {
                 const float2 w = make_float2(v[2 * k], v[2 * k + 1]);
 #pragma unroll
-                for (int r = 0; r < 6; ++r) acc[(k + r) % kChains] = __ffma2_rn(acc[(k + r) % kChains], w, w);
+                for (int r = 0; r < 6 * MIX; ++r) acc[(k + r) % kChains] = __ffma2_rn(acc[(k + r) % kChains], w, w);
             }
         }
     }
@@ -180,7 +183,7 @@ void run_force(const float4 *pos, float4 *partial, int n, Timer &t)
     const float ms = t.best([&] { kernel<<<grid, T>>>(args); }, 4);
     const double ginter = (double)n * n / (ms * 1e-3) / 1e9;
     printf("force %s P=%d T=%3d TJ=%3d U=%d minB=%2d regs=%3d occ=%2d blk/SM (%2d warps) cells=%5lld : %8.3f ms %8.1f G int/s %5.1f %% of %.2f TF\n",
-           ORDER == 0 ? "pair-major" : "op-major  ", P, T, TJ, U, MINB, fa.numRegs, occ, occ * T / 32, cells, ms, ginter,
+           ORDER == 0 ? "pair-major" : (ORDER == 2 ? "op-major  " : "crossed-sc"), P, T, TJ, U, MINB, fa.numRegs, occ, occ * T / 32, cells, ms, ginter,
            100.0 * ginter * 20.0 / 1e3 / g_peak_tflops, g_peak_tflops);
 }
 
@@ -228,13 +231,18 @@ int main(int argc, char **argv)
         report("FFMA  acc=fma(acc,a,b)          1 fetched reg", t.best([&] { mb_ffma<0><<<blocks, threads>>>(sink, input); }), per);
         report("FFMA  acc=fma(x[k],y[k],acc)    3 distinct regs (free allocation)", t.best([&] { mb_ffma<1><<<blocks, threads>>>(sink, input); }), per);
         report("FFMA  on halves of packed pairs  3 distinct regs, same parity", t.best([&] { mb_ffma<2><<<blocks, threads>>>(sink, input); }), per);
+        report("FFMA  on halves of packed pairs  acc halves crossed (e,e,o)/(o,o,e)", t.best([&] { mb_ffma<3><<<blocks, threads>>>(sink, input); }), per);
         const float ms = t.best([&] { mb_mufu<0><<<blocks, threads>>>((float *)sink, input); });
         const double per_clk_sm = 2.0 * kChains * kIters * (double)blocks * threads / (ms * 1e-3) / (clk_khz * 1e3) / g_sms;
         printf("%-66s %8.3f ms %7.2f MUFU.RSQ lanes/clk/SM\n", "MUFU.RSQ alone", ms, per_clk_sm);
         const float ms2 = t.best([&] { mb_mufu<1><<<blocks, threads>>>((float *)sink, input); });
         const double tf = 2.0 * (2.0 * 6 * kChains * kIters) * blocks * threads / (ms2 * 1e-3) / 1e12;
-        printf("%-66s %8.3f ms %7.2f TFLOP/s  %5.1f %% of peak (FFMA2 part)\n", "2 MUFU.RSQ + 6 FFMA2 (the n-body ratio)", ms2, tf,
+        printf("%-66s %8.3f ms %7.2f TFLOP/s  %5.1f %% of peak (FFMA2 part)\n", "2 MUFU.RSQ + 6 FFMA2 (XU-bound mix)", ms2, tf,
                100.0 * tf / g_peak_tflops);
+        const float ms3 = t.best([&] { mb_mufu<2><<<blocks, threads>>>((float *)sink, input); });
+        const double tf3 = 2.0 * (2.0 * 12 * kChains * kIters) * blocks * threads / (ms3 * 1e-3) / 1e12;
+        printf("%-66s %8.3f ms %7.2f TFLOP/s  %5.1f %% of peak (FFMA2 part)\n", "2 MUFU.RSQ + 12 FFMA2 (the n-body ratio)", ms3, tf3,
+               100.0 * tf3 / g_peak_tflops);
     }
 
     // ---- force kernel shapes at N bodies ----------------------------------------------------
@@ -248,18 +256,15 @@ int main(int argc, char **argv)
     CK(cudaMemcpy(pos, h.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
     printf("--- force_segments_kernel, N = %d, S = 8 ---\n", n);
     run_force<4, 256, 256, 8, 2, 0>(pos, partial, n, t);
-    run_force<4, 256, 256, 8, 1, 0>(pos, partial, n, t);
-    run_force<4, 128, 256, 8, 4, 0>(pos, partial, n, t);
-    run_force<2, 128, 256, 4, 4, 2>(pos, partial, n, t);
-    run_force<2, 128, 256, 4, 4, 0>(pos, partial, n, t);
-    run_force<2, 64, 64, 4, 8, 2>(pos, partial, n, t);
-    run_force<2, 64, 64, 8, 8, 0>(pos, partial, n, t);
-    run_force<1, 64, 64, 8, 16, 0>(pos, partial, n, t);
-    run_force<1, 64, 64, 4, 16, 0>(pos, partial, n, t);
-    run_force<1, 32, 64, 8, 32, 0>(pos, partial, n, t);
-    run_force<1, 32, 64, 4, 32, 0>(pos, partial, n, t);
-    run_force<2, 32, 64, 4, 16, 2>(pos, partial, n, t);
-    run_force<2, 32, 64, 8, 16, 0>(pos, partial, n, t);
+    run_force<4, 256, 256, 8, 2, 3>(pos, partial, n, t);
+    run_force<4, 256, 256, 4, 2, 3>(pos, partial, n, t);
+    run_force<4, 256, 256, 8, 1, 3>(pos, partial, n, t);
+    run_force<4, 128, 256, 8, 4, 3>(pos, partial, n, t);
+    run_force<2, 128, 256, 4, 4, 3>(pos, partial, n, t);
+    run_force<2, 128, 256, 8, 4, 3>(pos, partial, n, t);
+    run_force<8, 128, 256, 2, 2, 3>(pos, partial, n, t);
     run_force<8, 128, 256, 2, 2, 0>(pos, partial, n, t);
+    run_force<2, 64, 64, 8, 8, 3>(pos, partial, n, t);
+    run_force<1, 64, 64, 8, 16, 3>(pos, partial, n, t);
     return 0;
 }
