@@ -241,10 +241,14 @@ def run_mapc(args) -> None:
     launches0 = c.KernelLaunches()
     with ClockSampler(local_rank) as clocks:
         e0.record(stream)
-        for k in range(args.steps):
-            c.Simulate(n, 0, DT, DAMPING)
-            if k + 1 < args.steps:
-                l2_flush()
+        if args.batch > 1:
+            for k in range(0, args.steps, args.batch):
+                c.SimulateSteps(n, min(args.batch, args.steps - k), 0, DT, DAMPING)
+        else:
+            for k in range(args.steps):
+                c.Simulate(n, 0, DT, DAMPING)
+                if k + 1 < args.steps:
+                    l2_flush()
         c.Flush()
         e1.record(stream)
         c.WaitForGpu()
@@ -319,7 +323,7 @@ def run_mapc(args) -> None:
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"allpairs uniform sphere N={n} seed={SEED} dt={DT} damping={DAMPING}",
                        "n": n, "n_per_gpu": c.num_local, "plan": c.Plan(), "parallelism": f"i-shard x{world}" + (f" ({args.exchange} exchange)" if world > 1 else ""),
-                       "l2": "no flush (latency run)" if args.no_l2_flush else
+                       "batch": args.batch, "l2": "no flush (latency run)" if (args.no_l2_flush or args.batch > 1) else
                              "256 MiB memset between timed steps (inside the bracket)"},
             "step_us": {"min": float(step_ms.min() * 1e3), "median": float(np.median(step_ms) * 1e3),
                         "p99": float(np.percentile(step_ms, 99) * 1e3), "samples": int(step_ms.size)} if step_ms.size else None,
@@ -351,6 +355,8 @@ def main() -> None:
     ap.add_argument("--exchange", choices=["nccl", "peer"], default="nccl",
                     help="multi-GPU position exchange: NCCL all-gather, or direct peer-memory reads in the force kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=1,
+                    help="issue the timed steps in batches of this many (mapc_compute_simulate_steps); latency runs")
     ap.add_argument("--no-l2-flush", action="store_true",
                     help="latency runs (N = 10,000, config 2): no 256 MiB memset between steps")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline leg")

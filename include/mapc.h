@@ -158,6 +158,16 @@ MAPC_API mapc_status mapc_compute_simulate(mapc_compute *c, int num_active_parti
                                            float delta_time, float damping,
                                            uint64_t consumer_fence_value);
 
+/* `steps` consecutive Simulate calls in one submission (headless extension, no reference analogue):
+ * only the first step waits for the consumer fence and only the last one signals -- the fence jumps
+ * by `steps`, one value per step as if they had been issued one by one -- and the GPU timer records
+ * the batch average.  On an unsharded handle the force kernels of a batch are chained with
+ * programmatic dependent launch, so a step's grid is scheduled while the previous one drains.
+ * Same arithmetic, same bits as `steps` single calls. */
+MAPC_API mapc_status mapc_compute_simulate_steps(mapc_compute *c, int num_active_particles,
+                                                 float delta_time, float damping,
+                                                 uint64_t consumer_fence_value, int steps);
+
 /* UINT64 Compute::GetFenceValue() const, Compute.h:64: the value the NEXT Simulate signals */
 MAPC_API uint64_t    mapc_compute_fence_value(const mapc_compute *c);
 /* void Compute::WaitForGpu(), Compute.cpp:928-940: signal fence_value, fence_value++, host-wait */

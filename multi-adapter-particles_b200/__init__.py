@@ -67,7 +67,7 @@ EXPORTED_SYMBOLS = (
     "mapc_compute_step_times", "mapc_compute_flush",
     "mapc_consumer_create", "mapc_consumer_destroy", "mapc_consumer_draw", "mapc_consumer_latest",
     "mapc_consumer_wait_for_gpu", "mapc_consumer_counters",
-    "mapc_compute_ipc_export", "mapc_compute_ipc_attach",
+    "mapc_compute_ipc_export", "mapc_compute_ipc_attach", "mapc_compute_simulate_steps",
 )
 
 
@@ -159,6 +159,7 @@ def load() -> ctypes.CDLL:
         "mapc_consumer_counters": (c_int, [c_void_p, P(c_uint64)]),
         "mapc_compute_ipc_export": (c_int, [c_void_p, c_void_p]),
         "mapc_compute_ipc_attach": (c_int, [c_void_p, c_void_p, c_int]),
+        "mapc_compute_simulate_steps": (c_int, [c_void_p, c_int, c_float, c_float, c_uint64, c_int]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -297,6 +298,12 @@ class Compute:
         """``Compute::Simulate`` (Compute.cpp:1009-1055); asynchronous."""
         _check(self._lib.mapc_compute_simulate(self._h, in_numActiveParticles, deltaTime, damping,
                                                in_sharedFenceValue))
+
+    def SimulateSteps(self, in_numActiveParticles: int, steps: int, in_sharedFenceValue: int = 0,
+                      deltaTime: float = DEFAULT_DELTA_TIME, damping: float = DEFAULT_DAMPING) -> None:
+        """`steps` Simulate calls in one submission (mapc_compute_simulate_steps)."""
+        _check(self._lib.mapc_compute_simulate_steps(self._h, in_numActiveParticles, deltaTime, damping,
+                                                     in_sharedFenceValue, steps))
 
     def GetFenceValue(self) -> int:
         return int(self._lib.mapc_compute_fence_value(self._h))

@@ -368,12 +368,14 @@ struct mapc_compute {
     static constexpr float kAverageOver = 20.f;
     cudaEvent_t t_begin[kTimerSlots] = {}, t_end[kTimerSlots] = {};
     bool t_pending[kTimerSlots] = {};
+    int t_steps[kTimerSlots] = {};   // steps covered by the slot's event pair (batched Simulate)
     uint64_t t_next = 0, t_resolved = 0;
     float ms_average = 0.f, ms_last = 0.f;
     std::vector<float> step_log;  // raw samples not yet handed out by mapc_compute_step_times
 
     uint64_t launches = 0;
     bool has_state = false;
+    bool pdl_next = false;   // next force launch may overlap the previous one's tail (batched steps)
 };
 
 namespace {
@@ -387,6 +389,7 @@ void resolve_timers(mapc_compute *c, bool block)
             else if (cudaEventQuery(c->t_end[slot]) != cudaSuccess) return;
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, c->t_begin[slot], c->t_end[slot]) == cudaSuccess) {
+                if (c->t_steps[slot] > 1) ms /= (float)c->t_steps[slot];   // per-step average of a batch
                 // D3D12GpuTimer.h:151-153: t = (t*(N-1) + delta)/N
                 c->ms_average = (c->ms_average * (mapc_compute::kAverageOver - 1.f) + ms) /
                                 mapc_compute::kAverageOver;
@@ -405,7 +408,23 @@ template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER
 mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream_t stream)
 {
     dim3 grid((unsigned)args.n_iblocks, (unsigned)args.segs.count, 1);
-    mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER><<<grid, T, 0, stream>>>(args);
+    if (c->pdl_next) {
+        // batched steps: the grid may be scheduled while the previous step's grid drains (the kernel
+        // waits on griddepcontrol.wait before reading anything the previous step wrote)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(T, 1, 1);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MAPC_CUDA(cudaLaunchKernelEx(&cfg, mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER>, args));
+    } else {
+        mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER><<<grid, T, 0, stream>>>(args);
+    }
     MAPC_CUDA(cudaGetLastError());
     ++c->launches;
     return MAPC_OK;
@@ -766,15 +785,37 @@ mapc_status mapc_compute_set_force_mode(mapc_compute *c, mapc_force_mode mode)
 // ---- the step ---------------------------------------------------------------------------------
 // Enqueues one step on the compute (and comm) stream.  Runs either straight away or, when the
 // compute stream is gated on a consumer-fence value nobody has submitted yet, when that gate opens.
-static mapc_status enqueue_step(mapc_compute *c, uint32_t b, int n_targets, int n_sources, float delta_time,
-                                float damping, mapc_force_mode mode)
+static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n_sources, float delta_time,
+                               float damping, mapc_force_mode mode);
+
+// `steps` consecutive steps (ping-pong starting with write side b0) inside ONE timer pair.
+static mapc_status enqueue_steps(mapc_compute *c, uint32_t b0, int n_targets, int n_sources, float delta_time,
+                                 float damping, mapc_force_mode mode, int steps)
 {
-    const uint32_t r = 1u - b;  // read side (SURVEY section 3 C2: reads 1-b, writes b)
-    bool use_peer = false;
     resolve_timers(c, false);
     const int slot = (int)(c->t_next % mapc_compute::kTimerSlots);
     if (c->t_pending[slot]) resolve_timers(c, true);
     MAPC_CUDA(cudaEventRecord(c->t_begin[slot], c->compute));  // BeginTimer, Compute.cpp:1020
+    const bool pdl = steps > 1 && c->world == 1 && mode == MAPC_FORCE_ALLPAIRS && env_int("MAPC_FUSE", 1) != 0 &&
+                     env_int("MAPC_PDL", 1) != 0;
+    for (int k = 0; k < steps; ++k) {
+        c->pdl_next = pdl && k > 0;
+        const mapc_status st = enqueue_one(c, (b0 + (uint32_t)k) & 1u, n_targets, n_sources, delta_time, damping, mode);
+        c->pdl_next = false;
+        if (st != MAPC_OK) return st;
+    }
+    MAPC_CUDA(cudaEventRecord(c->t_end[slot], c->compute));  // EndTimer, Compute.cpp:1046
+    c->t_pending[slot] = true;
+    c->t_steps[slot] = steps;
+    ++c->t_next;
+    return MAPC_OK;
+}
+
+static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n_sources, float delta_time,
+                               float damping, mapc_force_mode mode)
+{
+    const uint32_t r = 1u - b;  // read side (SURVEY section 3 C2: reads 1-b, writes b)
+    bool use_peer = false;
 
     if (n_targets > 0) {
         if (mode == MAPC_FORCE_WELL) {
@@ -863,10 +904,6 @@ static mapc_status enqueue_step(mapc_compute *c, uint32_t b, int n_targets, int 
             }
         }
     }
-    MAPC_CUDA(cudaEventRecord(c->t_end[slot], c->compute));  // EndTimer, Compute.cpp:1046
-    c->t_pending[slot] = true;
-    ++c->t_next;
-
     if (c->world > 1 && c->peer_mode) {
         // Publish: this rank's positions of step step_id+1 are in place (and it has finished reading
         // everybody's previous ones).  A well-mode or zero-target step publishes too, so peers never wait.
@@ -892,7 +929,14 @@ static mapc_status enqueue_step(mapc_compute *c, uint32_t b, int n_targets, int 
 mapc_status mapc_compute_simulate(mapc_compute *c, int num_active_particles, float delta_time,
                                   float damping, uint64_t consumer_fence_value)
 {
+    return mapc_compute_simulate_steps(c, num_active_particles, delta_time, damping, consumer_fence_value, 1);
+}
+
+mapc_status mapc_compute_simulate_steps(mapc_compute *c, int num_active_particles, float delta_time,
+                                        float damping, uint64_t consumer_fence_value, int steps)
+{
     if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (steps < 1) return fail(MAPC_ERR_INVALID_ARGUMENT, "steps must be >= 1");
     if (num_active_particles < 0 || (uint32_t)num_active_particles > c->n)
         return fail(MAPC_ERR_INVALID_ARGUMENT, "num_active_particles %d outside [0, %u]",
                     num_active_particles, c->n);
@@ -908,13 +952,14 @@ mapc_status mapc_compute_simulate(mapc_compute *c, int num_active_particles, flo
     const int n_sources = num_active_particles;
     const mapc_force_mode mode = c->mode;
     MAPC_TRY(mapc::gs_call(&c->gcompute, [=]() -> mapc_status {
-        return enqueue_step(c, b, n_targets, n_sources, delta_time, damping, mode);
+        return enqueue_steps(c, b, n_targets, n_sources, delta_time, damping, mode, steps);
     }));
 
-    // MoveToNextFrame, Compute.cpp:993-1004
+    // MoveToNextFrame, Compute.cpp:993-1004 (a batch consumes one fence value per step and signals the last)
+    c->fence_value += (uint64_t)(steps - 1);
     MAPC_TRY(mapc::gs_signal(&c->gcompute, c->fence, c->fence_value));
     c->fence_value++;
-    c->buffer_index = 1u - c->buffer_index;
+    if (steps & 1) c->buffer_index = 1u - c->buffer_index;
     return MAPC_OK;
 }
 

@@ -224,6 +224,11 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
     const int tid = threadIdx.x;
     const float4 *__restrict__ pos = a.pos;
     const float4 *__restrict__ src = PEER ? a.seg_src[blockIdx.y] : a.pos;   // where this cell's sources live
+    // Programmatic dependent launch (batched steps): let the next step's grid start filling SMs as this
+    // one drains, and do not touch the previous step's output before that grid has completely finished.
+    // Both are no-ops for a launch without the programmatic-serialization attribute.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (PEER) {
         const unsigned long long *flag = a.seg_flag[blockIdx.y];
         if (flag != nullptr) {

@@ -330,3 +330,22 @@ def test_headless_consumer_frame_loop(mapc, oracle, gpu):
                 assert np.abs(pos[:, :3] - ref[:, :3]).max() / scale <= TOL_10, frame
             final = c.Download()
             assert_close(oracle, final, states[6], TOL_10, "producer state after 6 frames")
+
+
+def test_batched_steps_equal_single_steps(mapc, gpu):
+    """mapc_compute_simulate_steps (programmatic dependent launch between the steps of a batch) must
+    give the bits of the same number of single Simulate calls, and keep the fence numbering."""
+    n = 10_000
+    p = mapc.ic.workload("interactive_10k")
+    single = gpu_steps(mapc, p, 7)
+    with mapc.Compute(n, 0) as c:
+        c.Upload(p)
+        f0 = c.GetFenceValue()
+        c.SimulateSteps(n, 4)
+        assert c.GetFenceValue() == f0 + 4
+        c.SimulateSteps(n, 3)
+        assert c.GetFenceValue() == f0 + 7
+        c.GetSharedHandles().m_fence.Wait(f0 + 6)
+        c.WaitForGpu()
+        assert c.Download().tobytes() == single.tobytes()
+        assert c.GetSharedHandles().m_bufferIndex == 1      # 7 steps: odd number of flips
