@@ -344,6 +344,7 @@ struct mapc_compute {
     float4 *packed[2] = {nullptr, nullptr};         // packed positions, all N, per side
     float4 *partial = nullptr;                      // [segments][n_local]
     int partial_segments = 0;
+    mapc_posvelo *upload_stage = nullptr;           // sharded handles: landing buffer of Upload (all N)
     unsigned *counters = nullptr;                   // per target block: segments finished this step
     int counters_key = 0;                           // block size the counters were last used with
 
@@ -702,6 +703,7 @@ mapc_status mapc_compute_destroy(mapc_compute *c)
     }
     if (c->partial) cudaFree(c->partial);
     if (c->counters) cudaFree(c->counters);
+    if (c->upload_stage) cudaFree(c->upload_stage);
     if (c->ev_integrated) cudaEventDestroy(c->ev_integrated);
     for (int k = 0; k < mapc_compute::kTimerSlots; ++k) {
         if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]);
@@ -725,29 +727,28 @@ mapc_status mapc_compute_upload(mapc_compute *c, const mapc_posvelo *host, uint3
     if (n != c->n) return fail(MAPC_ERR_INVALID_ARGUMENT, "upload of %u bodies into a handle of %u", n, c->n);
     MAPC_TRY(mapc::require_ungated(&c->gcompute, "Upload"));
     DeviceGuard g(c->device);
-    // stage all N bodies once (side 1's packed array is big enough only for positions, so use a
-    // temporary), then fan out: both PosVelo sides get the shard, both packed sides all N.
-    mapc_posvelo *tmp = nullptr;
-    MAPC_CUDA(cudaMalloc(&tmp, (size_t)n * sizeof(mapc_posvelo)));
-    mapc_status st = [&]() -> mapc_status {
-        MAPC_CUDA(cudaMemcpyAsync(tmp, host, (size_t)n * sizeof(mapc_posvelo), cudaMemcpyHostToDevice,
-                                  c->compute));
-        for (int s = 0; s < 2; ++s) {
-            MAPC_CUDA(cudaMemcpyAsync(c->posvelo[s], tmp + c->i_first,
-                                      (size_t)c->n_local * sizeof(mapc_posvelo),
+    // All N bodies land on the device once, then fan out: both PosVelo sides get the shard, both packed
+    // sides all N positions.  Unsharded, side 0 itself is the landing buffer; a sharded handle keeps a
+    // staging buffer for the bodies it does not own (allocated on first use, reused afterwards).
+    mapc_posvelo *all = c->posvelo[0];
+    if (c->world > 1) {
+        if (!c->upload_stage) MAPC_CUDA(cudaMalloc(&c->upload_stage, (size_t)n * sizeof(mapc_posvelo)));
+        all = c->upload_stage;
+    }
+    MAPC_CUDA(cudaMemcpyAsync(all, host, (size_t)n * sizeof(mapc_posvelo), cudaMemcpyHostToDevice, c->compute));
+    for (int s = 0; s < 2; ++s) {
+        if (c->posvelo[s] != all)
+            MAPC_CUDA(cudaMemcpyAsync(c->posvelo[s], all + c->i_first, (size_t)c->n_local * sizeof(mapc_posvelo),
                                       cudaMemcpyDeviceToDevice, c->compute));
-            mapc::pack_positions_kernel<<<(n + 255) / 256, 256, 0, c->compute>>>(tmp, c->packed[s], (int)n);
-            MAPC_CUDA(cudaGetLastError());
-            ++c->launches;
-        }
-        c->gather_pending[0] = c->gather_pending[1] = false;
-        MAPC_CUDA(cudaStreamSynchronize(c->comm));
-        return MAPC_OK;
-    }();
-    if (st == MAPC_OK) st = mapc_compute_wait_for_gpu(c);  // Compute.cpp:922
-    cudaFree(tmp);
-    if (st == MAPC_OK) c->has_state = true;
-    return st;
+        mapc::pack_positions_kernel<<<(n + 255) / 256, 256, 0, c->compute>>>(all, c->packed[s], (int)n);
+        MAPC_CUDA(cudaGetLastError());
+        ++c->launches;
+    }
+    MAPC_CUDA(cudaStreamSynchronize(c->comm));
+    c->gather_pending[0] = c->gather_pending[1] = false;
+    MAPC_TRY(mapc_compute_wait_for_gpu(c));  // InitializeParticles ends with WaitForGpu, Compute.cpp:922
+    c->has_state = true;
+    return MAPC_OK;
 }
 
 mapc_status mapc_compute_download(mapc_compute *c, mapc_posvelo *host, uint32_t first, uint32_t count)

@@ -26,3 +26,39 @@ def test_sharded_equals_unsharded_bitwise(mapc, gpu):
     sys.stderr.write(res.stderr[-4000:])
     assert res.returncode == 0
     assert "bit-identical=True" in res.stdout and "bit-identical=False" not in res.stdout
+
+
+def test_cross_device_consumer_and_migration(mapc, oracle, gpu):
+    """The reference's headline scenario: producer and consumer on different adapters
+    (Render.cpp:789-831 copies across devices) and live migration of the simulation to another
+    device (Particles.cpp:512-522 -> Compute(n, adapter, ext, prev) -> CopyState, Compute.cpp:303-410)."""
+    if gpu < 2:
+        pytest.skip("needs at least 2 visible GPUs (run with gpurun --gpus 2)")
+    import numpy as np
+    n = 4096
+    p = mapc.ic.lattice_sphere(n, 1500.0, seed=3, speed=1.0)
+    ref = [p]
+    for _ in range(8):
+        ref.append(oracle.step_allpairs(ref[-1], flavour=oracle.MIRRORED))
+    with mapc.Compute(n, 0) as a:
+        a.Upload(p)
+        with mapc.Consumer(a, 1) as r:                      # consumer on the other device
+            for _ in range(4):
+                f = a.GetFenceValue()
+                f = r.Draw(n, f, n)
+                a.Simulate(n, f)
+            a.WaitForGpu(); r.WaitForGpu()
+            frame, pos = r.Latest()
+            assert frame == 2                               # frame k shows step k-2 (two-buffer latency)
+            scale = np.abs(ref[frame]["pos"][:, :3]).max()
+            assert np.abs(pos[:, :3] - ref[frame]["pos"][:, :3]).max() / scale <= 1e-5
+        state4 = a.Download()
+        with mapc.Compute(n, 1, a) as b:                    # migrate to device 1
+            assert b.Download().tobytes() == state4.tobytes()
+            for _ in range(4):
+                a.Simulate(n, 0)
+                b.Simulate(n, 0)
+            a.WaitForGpu(); b.WaitForGpu()
+            assert b.Download().tobytes() == a.Download().tobytes()   # same trajectory, bit for bit
+            err = oracle.rel_errors(b.Download(), ref[8])
+            assert max(err.values()) <= 1e-4, err
