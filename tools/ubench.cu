@@ -255,16 +255,158 @@ int main(int argc, char **argv)
     CK(cudaMalloc(&partial, sizeof(float4) * n * 8));
     CK(cudaMemcpy(pos, h.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
     printf("--- force_segments_kernel, N = %d, S = 8 ---\n", n);
+#ifdef SWEEP_BROAD
+    run_force<4, 256, 256, 1, 2, 0>(pos, partial, n, t);
+    run_force<4, 256, 256, 1, 3, 0>(pos, partial, n, t);
+    run_force<4, 256, 256, 2, 2, 0>(pos, partial, n, t);
+    run_force<4, 256, 256, 2, 3, 0>(pos, partial, n, t);
+    run_force<4, 256, 256, 4, 2, 0>(pos, partial, n, t);
+    run_force<4, 256, 256, 4, 3, 0>(pos, partial, n, t);
     run_force<4, 256, 256, 8, 2, 0>(pos, partial, n, t);
-    run_force<4, 256, 256, 8, 2, 3>(pos, partial, n, t);
-    run_force<4, 256, 256, 4, 2, 3>(pos, partial, n, t);
-    run_force<4, 256, 256, 8, 1, 3>(pos, partial, n, t);
-    run_force<4, 128, 256, 8, 4, 3>(pos, partial, n, t);
-    run_force<2, 128, 256, 4, 4, 3>(pos, partial, n, t);
-    run_force<2, 128, 256, 8, 4, 3>(pos, partial, n, t);
-    run_force<8, 128, 256, 2, 2, 3>(pos, partial, n, t);
-    run_force<8, 128, 256, 2, 2, 0>(pos, partial, n, t);
-    run_force<2, 64, 64, 8, 8, 3>(pos, partial, n, t);
-    run_force<1, 64, 64, 8, 16, 3>(pos, partial, n, t);
+    run_force<4, 256, 256, 8, 3, 0>(pos, partial, n, t);
+    run_force<4, 128, 256, 1, 4, 0>(pos, partial, n, t);
+    run_force<4, 128, 256, 1, 6, 0>(pos, partial, n, t);
+    run_force<4, 128, 256, 2, 4, 0>(pos, partial, n, t);
+    run_force<4, 128, 256, 2, 6, 0>(pos, partial, n, t);
+    run_force<4, 128, 256, 4, 4, 0>(pos, partial, n, t);
+    run_force<4, 128, 256, 4, 6, 0>(pos, partial, n, t);
+    run_force<4, 128, 256, 8, 4, 0>(pos, partial, n, t);
+    run_force<4, 128, 256, 8, 6, 0>(pos, partial, n, t);
+    run_force<2, 256, 256, 1, 2, 0>(pos, partial, n, t);
+    run_force<2, 256, 256, 1, 4, 0>(pos, partial, n, t);
+    run_force<2, 256, 256, 2, 2, 0>(pos, partial, n, t);
+    run_force<2, 256, 256, 2, 4, 0>(pos, partial, n, t);
+    run_force<2, 256, 256, 4, 2, 0>(pos, partial, n, t);
+    run_force<2, 256, 256, 4, 4, 0>(pos, partial, n, t);
+    run_force<2, 256, 256, 8, 2, 0>(pos, partial, n, t);
+    run_force<2, 256, 256, 8, 4, 0>(pos, partial, n, t);
+    run_force<2, 128, 256, 1, 4, 0>(pos, partial, n, t);
+    run_force<2, 128, 256, 1, 8, 0>(pos, partial, n, t);
+    run_force<2, 128, 256, 2, 4, 0>(pos, partial, n, t);
+    run_force<2, 128, 256, 2, 8, 0>(pos, partial, n, t);
+    run_force<2, 128, 256, 4, 4, 0>(pos, partial, n, t);
+    run_force<2, 128, 256, 4, 8, 0>(pos, partial, n, t);
+    run_force<2, 128, 256, 8, 4, 0>(pos, partial, n, t);
+    run_force<2, 128, 256, 8, 8, 0>(pos, partial, n, t);
+    run_force<1, 256, 256, 1, 4, 0>(pos, partial, n, t);
+    run_force<1, 256, 256, 1, 6, 0>(pos, partial, n, t);
+    run_force<1, 256, 256, 1, 8, 0>(pos, partial, n, t);
+    run_force<1, 256, 256, 2, 4, 0>(pos, partial, n, t);
+    run_force<1, 256, 256, 2, 6, 0>(pos, partial, n, t);
+    run_force<1, 256, 256, 2, 8, 0>(pos, partial, n, t);
+    run_force<1, 256, 256, 4, 4, 0>(pos, partial, n, t);
+    run_force<1, 256, 256, 4, 6, 0>(pos, partial, n, t);
+    run_force<1, 256, 256, 4, 8, 0>(pos, partial, n, t);
+    run_force<1, 256, 256, 8, 4, 0>(pos, partial, n, t);
+    run_force<1, 256, 256, 8, 6, 0>(pos, partial, n, t);
+    run_force<1, 256, 256, 8, 8, 0>(pos, partial, n, t);
+    run_force<1, 128, 256, 1, 8, 0>(pos, partial, n, t);
+    run_force<1, 128, 256, 1, 12, 0>(pos, partial, n, t);
+    run_force<1, 128, 256, 1, 16, 0>(pos, partial, n, t);
+    run_force<1, 128, 256, 2, 8, 0>(pos, partial, n, t);
+    run_force<1, 128, 256, 2, 12, 0>(pos, partial, n, t);
+    run_force<1, 128, 256, 2, 16, 0>(pos, partial, n, t);
+    run_force<1, 128, 256, 4, 8, 0>(pos, partial, n, t);
+    run_force<1, 128, 256, 4, 12, 0>(pos, partial, n, t);
+    run_force<1, 128, 256, 4, 16, 0>(pos, partial, n, t);
+    run_force<1, 128, 256, 8, 8, 0>(pos, partial, n, t);
+    run_force<1, 128, 256, 8, 12, 0>(pos, partial, n, t);
+    run_force<1, 128, 256, 8, 16, 0>(pos, partial, n, t);
+    run_force<2, 64, 64, 1, 8, 0>(pos, partial, n, t);
+    run_force<2, 64, 64, 1, 16, 0>(pos, partial, n, t);
+    run_force<2, 64, 64, 2, 8, 0>(pos, partial, n, t);
+    run_force<2, 64, 64, 2, 16, 0>(pos, partial, n, t);
+    run_force<2, 64, 64, 4, 8, 0>(pos, partial, n, t);
+    run_force<2, 64, 64, 4, 16, 0>(pos, partial, n, t);
+    run_force<2, 64, 64, 8, 8, 0>(pos, partial, n, t);
+    run_force<2, 64, 64, 8, 16, 0>(pos, partial, n, t);
+    run_force<1, 64, 64, 1, 16, 0>(pos, partial, n, t);
+    run_force<1, 64, 64, 1, 24, 0>(pos, partial, n, t);
+    run_force<1, 64, 64, 2, 16, 0>(pos, partial, n, t);
+    run_force<1, 64, 64, 2, 24, 0>(pos, partial, n, t);
+    run_force<1, 64, 64, 4, 16, 0>(pos, partial, n, t);
+    run_force<1, 64, 64, 4, 24, 0>(pos, partial, n, t);
+    run_force<1, 64, 64, 8, 16, 0>(pos, partial, n, t);
+    run_force<1, 64, 64, 8, 24, 0>(pos, partial, n, t);
+    run_force<4, 256, 256, 1, 2, 2>(pos, partial, n, t);
+    run_force<4, 256, 256, 1, 3, 2>(pos, partial, n, t);
+    run_force<4, 256, 256, 2, 2, 2>(pos, partial, n, t);
+    run_force<4, 256, 256, 2, 3, 2>(pos, partial, n, t);
+    run_force<4, 256, 256, 4, 2, 2>(pos, partial, n, t);
+    run_force<4, 256, 256, 4, 3, 2>(pos, partial, n, t);
+    run_force<4, 256, 256, 8, 2, 2>(pos, partial, n, t);
+    run_force<4, 256, 256, 8, 3, 2>(pos, partial, n, t);
+    run_force<4, 128, 256, 1, 4, 2>(pos, partial, n, t);
+    run_force<4, 128, 256, 1, 6, 2>(pos, partial, n, t);
+    run_force<4, 128, 256, 2, 4, 2>(pos, partial, n, t);
+    run_force<4, 128, 256, 2, 6, 2>(pos, partial, n, t);
+    run_force<4, 128, 256, 4, 4, 2>(pos, partial, n, t);
+    run_force<4, 128, 256, 4, 6, 2>(pos, partial, n, t);
+    run_force<4, 128, 256, 8, 4, 2>(pos, partial, n, t);
+    run_force<4, 128, 256, 8, 6, 2>(pos, partial, n, t);
+    run_force<2, 256, 256, 1, 2, 2>(pos, partial, n, t);
+    run_force<2, 256, 256, 1, 4, 2>(pos, partial, n, t);
+    run_force<2, 256, 256, 2, 2, 2>(pos, partial, n, t);
+    run_force<2, 256, 256, 2, 4, 2>(pos, partial, n, t);
+    run_force<2, 256, 256, 4, 2, 2>(pos, partial, n, t);
+    run_force<2, 256, 256, 4, 4, 2>(pos, partial, n, t);
+    run_force<2, 256, 256, 8, 2, 2>(pos, partial, n, t);
+    run_force<2, 256, 256, 8, 4, 2>(pos, partial, n, t);
+    run_force<2, 128, 256, 1, 4, 2>(pos, partial, n, t);
+    run_force<2, 128, 256, 1, 8, 2>(pos, partial, n, t);
+    run_force<2, 128, 256, 2, 4, 2>(pos, partial, n, t);
+    run_force<2, 128, 256, 2, 8, 2>(pos, partial, n, t);
+    run_force<2, 128, 256, 4, 4, 2>(pos, partial, n, t);
+    run_force<2, 128, 256, 4, 8, 2>(pos, partial, n, t);
+    run_force<2, 128, 256, 8, 4, 2>(pos, partial, n, t);
+    run_force<2, 128, 256, 8, 8, 2>(pos, partial, n, t);
+    run_force<1, 256, 256, 1, 4, 2>(pos, partial, n, t);
+    run_force<1, 256, 256, 1, 6, 2>(pos, partial, n, t);
+    run_force<1, 256, 256, 1, 8, 2>(pos, partial, n, t);
+    run_force<1, 256, 256, 2, 4, 2>(pos, partial, n, t);
+    run_force<1, 256, 256, 2, 6, 2>(pos, partial, n, t);
+    run_force<1, 256, 256, 2, 8, 2>(pos, partial, n, t);
+    run_force<1, 256, 256, 4, 4, 2>(pos, partial, n, t);
+    run_force<1, 256, 256, 4, 6, 2>(pos, partial, n, t);
+    run_force<1, 256, 256, 4, 8, 2>(pos, partial, n, t);
+    run_force<1, 256, 256, 8, 4, 2>(pos, partial, n, t);
+    run_force<1, 256, 256, 8, 6, 2>(pos, partial, n, t);
+    run_force<1, 256, 256, 8, 8, 2>(pos, partial, n, t);
+    run_force<1, 128, 256, 1, 8, 2>(pos, partial, n, t);
+    run_force<1, 128, 256, 1, 12, 2>(pos, partial, n, t);
+    run_force<1, 128, 256, 1, 16, 2>(pos, partial, n, t);
+    run_force<1, 128, 256, 2, 8, 2>(pos, partial, n, t);
+    run_force<1, 128, 256, 2, 12, 2>(pos, partial, n, t);
+    run_force<1, 128, 256, 2, 16, 2>(pos, partial, n, t);
+    run_force<1, 128, 256, 4, 8, 2>(pos, partial, n, t);
+    run_force<1, 128, 256, 4, 12, 2>(pos, partial, n, t);
+    run_force<1, 128, 256, 4, 16, 2>(pos, partial, n, t);
+    run_force<1, 128, 256, 8, 8, 2>(pos, partial, n, t);
+    run_force<1, 128, 256, 8, 12, 2>(pos, partial, n, t);
+    run_force<1, 128, 256, 8, 16, 2>(pos, partial, n, t);
+    run_force<2, 64, 64, 1, 8, 2>(pos, partial, n, t);
+    run_force<2, 64, 64, 1, 16, 2>(pos, partial, n, t);
+    run_force<2, 64, 64, 2, 8, 2>(pos, partial, n, t);
+    run_force<2, 64, 64, 2, 16, 2>(pos, partial, n, t);
+    run_force<2, 64, 64, 4, 8, 2>(pos, partial, n, t);
+    run_force<2, 64, 64, 4, 16, 2>(pos, partial, n, t);
+    run_force<2, 64, 64, 8, 8, 2>(pos, partial, n, t);
+    run_force<2, 64, 64, 8, 16, 2>(pos, partial, n, t);
+    run_force<1, 64, 64, 1, 16, 2>(pos, partial, n, t);
+    run_force<1, 64, 64, 1, 24, 2>(pos, partial, n, t);
+    run_force<1, 64, 64, 2, 16, 2>(pos, partial, n, t);
+    run_force<1, 64, 64, 2, 24, 2>(pos, partial, n, t);
+    run_force<1, 64, 64, 4, 16, 2>(pos, partial, n, t);
+    run_force<1, 64, 64, 4, 24, 2>(pos, partial, n, t);
+    run_force<1, 64, 64, 8, 16, 2>(pos, partial, n, t);
+    run_force<1, 64, 64, 8, 24, 2>(pos, partial, n, t);
+#else
+    run_force<4, 256, 256, 8, 2, 0>(pos, partial, n, t);
+    run_force<4, 128, 256, 8, 4, 0>(pos, partial, n, t);
+    run_force<2, 128, 256, 4, 4, 2>(pos, partial, n, t);
+    run_force<2, 64, 64, 4, 8, 2>(pos, partial, n, t);
+    run_force<1, 64, 64, 8, 16, 0>(pos, partial, n, t);
+    run_force<1, 32, 64, 8, 32, 0>(pos, partial, n, t);
+#endif
     return 0;
 }
