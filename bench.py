@@ -254,6 +254,7 @@ def run_mapc(args) -> None:
         c.WaitForGpu()
         barrier()
     launches = c.KernelLaunches() - launches0
+    gather_ms, gather_tail_ms = c.ExchangeTimes() if world > 1 else (0.0, 0.0)
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     step_ms = c.StepTimes()
     kernel_ms = max_over_ranks(float(np.mean(step_ms))) if step_ms.size else float("nan")
@@ -334,6 +335,10 @@ def run_mapc(args) -> None:
                     "d2h_bytes_per_step": int(c.num_local * 32 * world), "ms_per_step": e2e_s * 1e3,
                     "steps": e2e_steps, "checksum": checksum},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "exchange": ({"kind": args.exchange, "allgather_ms": gather_ms,
+                          "allgather_past_step_begin_ms": gather_tail_ms,
+                          "note": "the gather of step k's positions runs under the local cells of step k+1"}
+                         if world > 1 else None),
         }
     c.close()
     if world > 1:

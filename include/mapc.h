@@ -200,6 +200,11 @@ MAPC_API mapc_status mapc_compute_gpu_times(mapc_compute *c, float *ms_average, 
  * `capacity`; the log keeps the latest 4096).  Lets a benchmark average the device time of the
  * steps it issued without synchronising between them. */
 MAPC_API mapc_status mapc_compute_step_times(mapc_compute *c, float *ms_out, int capacity, int *count);
+/* Sharded handles, NCCL exchange: duration of the newest completed position all-gather, and how long it
+ * was still running after the step that consumes it had begun (<= 0: finished before; > 0: the remote
+ * cells of that step started this late -- the local cells ran meanwhile).  Evidence of the overlap. */
+MAPC_API mapc_status mapc_compute_exchange_times(mapc_compute *c, float *gather_ms,
+                                                 float *tail_past_step_begin_ms);
 /* Make the compute stream wait for the exchange (all-gather) work issued so far, without blocking
  * the host: an event recorded on compute_stream afterwards covers the whole step. */
 MAPC_API mapc_status mapc_compute_flush(mapc_compute *c);

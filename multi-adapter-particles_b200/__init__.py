@@ -68,6 +68,7 @@ EXPORTED_SYMBOLS = (
     "mapc_consumer_create", "mapc_consumer_destroy", "mapc_consumer_draw", "mapc_consumer_latest",
     "mapc_consumer_wait_for_gpu", "mapc_consumer_counters",
     "mapc_compute_ipc_export", "mapc_compute_ipc_attach", "mapc_compute_simulate_steps",
+    "mapc_compute_exchange_times",
 )
 
 
@@ -160,6 +161,7 @@ def load() -> ctypes.CDLL:
         "mapc_compute_ipc_export": (c_int, [c_void_p, c_void_p]),
         "mapc_compute_ipc_attach": (c_int, [c_void_p, c_void_p, c_int]),
         "mapc_compute_simulate_steps": (c_int, [c_void_p, c_int, c_float, c_float, c_uint64, c_int]),
+        "mapc_compute_exchange_times": (c_int, [c_void_p, P(c_float), P(c_float)]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -370,6 +372,12 @@ class Compute:
         cnt = c_int(0)
         _check(self._lib.mapc_compute_step_times(self._h, buf, capacity, byref(cnt)))
         return np.array(buf[:cnt.value], dtype=np.float32)
+
+    def ExchangeTimes(self):
+        """(all-gather ms, ms it ran past the start of the consuming step) for the newest completed gather."""
+        a, b = c_float(0), c_float(0)
+        _check(self._lib.mapc_compute_exchange_times(self._h, byref(a), byref(b)))
+        return a.value, b.value
 
     def Flush(self) -> None:
         _check(self._lib.mapc_compute_flush(self._h))

@@ -34,6 +34,7 @@ struct GatedStream;
 struct FenceSignal {
     uint64_t value;
     cudaEvent_t event;
+    int device;   // device the event was created on
 };
 
 }  // namespace mapc
@@ -43,6 +44,8 @@ struct mapc_fence {
     uint64_t submitted = 0;             // highest value whose signal has been submitted
     std::deque<mapc::FenceSignal> signals;        // submitted stream signals, ascending, not yet pruned
     std::vector<mapc::GatedStream *> waiters;     // streams gated on a value of this fence
+    std::vector<cudaEvent_t> spare;               // completed signals' events, reused instead of re-created
+    std::vector<int> spare_device;
 };
 
 namespace mapc {

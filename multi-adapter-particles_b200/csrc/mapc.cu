@@ -158,11 +158,19 @@ mapc_status fence_submit_signal(mapc_fence *f, cudaStream_t stream, int device, 
     // drop signals that have completed (their waits are no-ops from now on)
     const uint64_t done = fence_completed(f);
     while (f->signals.size() > 4 && f->signals.front().value <= done) {
-        cudaEventDestroy(f->signals.front().event);
+        f->spare.push_back(f->signals.front().event);   // recycled by a later signal from the same device
+        f->spare_device.push_back(f->signals.front().device);
         f->signals.pop_front();
     }
     cudaEvent_t ev = nullptr;
-    MAPC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (size_t k = 0; k < f->spare.size(); ++k)
+        if (f->spare_device[k] == device) {
+            ev = f->spare[k];
+            f->spare.erase(f->spare.begin() + (long)k);
+            f->spare_device.erase(f->spare_device.begin() + (long)k);
+            break;
+        }
+    if (!ev) MAPC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     MAPC_CUDA(cudaEventRecord(ev, stream));
     const CUresult r = g_write64((CUstream)stream, (CUdeviceptr)(uintptr_t)f->word, value,
                                  CU_STREAM_WRITE_VALUE_DEFAULT);
@@ -170,7 +178,7 @@ mapc_status fence_submit_signal(mapc_fence *f, cudaStream_t stream, int device, 
         cudaEventDestroy(ev);
         return fail(MAPC_ERR_CUDA, "cuStreamWriteValue64 failed: %d", (int)r);
     }
-    f->signals.push_back(FenceSignal{value, ev});
+    f->signals.push_back(FenceSignal{value, ev, device});
     if (value > f->submitted) f->submitted = value;
     fence_notify(f);
     return MAPC_OK;
@@ -361,7 +369,9 @@ struct mapc_compute {
     unsigned long long *peer_flag[16] = {};
     unsigned long long step_id = 0;              // steps issued since attach (same on every rank)
     cudaEvent_t ev_integrated = nullptr;
-    cudaEvent_t ev_gathered[2] = {nullptr, nullptr};
+    cudaEvent_t ev_gathered[2] = {nullptr, nullptr};     // timing-enabled: also the end of the gather
+    cudaEvent_t ev_gather_begin[2] = {nullptr, nullptr};
+
     bool gather_pending[2] = {false, false};
 
     // "simulate ms" timer (Compute.cpp:445-446, D3D12GpuTimer.h:151-153)
@@ -508,7 +518,8 @@ mapc_status create_common(mapc_compute **out, uint32_t n, int device, int rank, 
         for (int s = 0; s < 2; ++s) {
             MAPC_CUDA(cudaMalloc(&c->posvelo[s], (size_t)c->n_local * sizeof(mapc_posvelo)));
             MAPC_CUDA(cudaMalloc(&c->packed[s], (size_t)n * sizeof(float4)));
-            MAPC_CUDA(cudaEventCreateWithFlags(&c->ev_gathered[s], cudaEventDisableTiming));
+            MAPC_CUDA(cudaEventCreate(&c->ev_gathered[s]));
+            MAPC_CUDA(cudaEventCreate(&c->ev_gather_begin[s]));
         }
         MAPC_CUDA(cudaEventCreateWithFlags(&c->ev_integrated, cudaEventDisableTiming));
         for (int k = 0; k < mapc_compute::kTimerSlots; ++k) {
@@ -586,6 +597,7 @@ mapc_status mapc_fence_destroy(mapc_fence *f)
     f->submitted = UINT64_MAX;
     mapc::fence_notify(f);
     for (mapc::FenceSignal &sig : f->signals) cudaEventDestroy(sig.event);
+    for (cudaEvent_t ev : f->spare) cudaEventDestroy(ev);
     if (f->word) cudaFreeHost((void *)f->word);
     delete f;
     return MAPC_OK;
@@ -700,6 +712,7 @@ mapc_status mapc_compute_destroy(mapc_compute *c)
         if (c->posvelo[s]) cudaFree(c->posvelo[s]);
         if (c->packed[s]) cudaFree(c->packed[s]);
         if (c->ev_gathered[s]) cudaEventDestroy(c->ev_gathered[s]);
+        if (c->ev_gather_begin[s]) cudaEventDestroy(c->ev_gather_begin[s]);
     }
     if (c->partial) cudaFree(c->partial);
     if (c->counters) cudaFree(c->counters);
@@ -919,6 +932,7 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
         if (c->gather_pending[r]) MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_gathered[r], 0));
         MAPC_CUDA(cudaEventRecord(c->ev_integrated, c->compute));
         MAPC_CUDA(cudaStreamWaitEvent(c->comm, c->ev_integrated, 0));
+        MAPC_CUDA(cudaEventRecord(c->ev_gather_begin[b], c->comm));
         MAPC_NCCL(g_nccl.AllGather(c->packed[b] + c->i_first, c->packed[b], (size_t)c->n_local * 4,
                                    ncclFloat, c->nccl, c->comm));
         MAPC_CUDA(cudaEventRecord(c->ev_gathered[b], c->comm));
@@ -1072,6 +1086,28 @@ mapc_status mapc_compute_ipc_attach(mapc_compute *c, const void *blobs_all_ranks
     c->peer_mode = true;
     c->step_id = 0;
     c->gather_pending[0] = c->gather_pending[1] = false;
+    return MAPC_OK;
+}
+
+mapc_status mapc_compute_exchange_times(mapc_compute *c, float *gather_ms, float *tail_past_step_begin_ms)
+{
+    if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (gather_ms) *gather_ms = 0.f;
+    if (tail_past_step_begin_ms) *tail_past_step_begin_ms = 0.f;
+    if (c->world < 2 || c->peer_mode) return MAPC_OK;
+    DeviceGuard g(c->device);
+    // the newest gather that has completed: the one into the side the last step READ, i.e. issued by the
+    // step before it; the last step's timer slot gives the begin of the step that consumed it
+    if (c->t_next < 2) return MAPC_OK;
+    const uint32_t side = c->buffer_index;   // last step wrote 1-buffer_index... and read buffer_index
+    if (cudaEventQuery(c->ev_gathered[side]) != cudaSuccess) return MAPC_OK;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_gather_begin[side], c->ev_gathered[side]) == cudaSuccess && gather_ms)
+        *gather_ms = ms;
+    const int slot = (int)((c->t_next - 1) % mapc_compute::kTimerSlots);
+    if (cudaEventQuery(c->t_end[slot]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, c->t_begin[slot], c->ev_gathered[side]) == cudaSuccess && tail_past_step_begin_ms)
+        *tail_past_step_begin_ms = ms;   // > 0: the gather was still running this long into the consuming step
     return MAPC_OK;
 }
 

@@ -86,3 +86,43 @@ def test_ic_generators_are_deterministic(mapc):
     rp = np.linalg.norm(p["pos"][:, :3], axis=1)
     assert rp.max() <= 500.0 * (1 + 1e-5)
     assert 30.0 < np.median(rp) < 90.0   # Plummer half-mass radius ~ 1.3 a
+
+
+def test_missing_extension_fails_loudly(mapc, monkeypatch, tmp_path):
+    """No silent fallback: if libmapc.so is not there, loading the product raises."""
+    monkeypatch.setattr(mapc, "_lib", None)
+    monkeypatch.setattr(mapc, "LIB_PATH", str(tmp_path / "libmapc.so"))
+    with pytest.raises(ImportError):
+        mapc.load()
+    with pytest.raises(ImportError):
+        mapc.Compute(64, 0)
+
+
+def test_header_is_plain_c_and_links(mapc, tmp_path):
+    """include/mapc.h must be usable from C (the reference-side binding is C/C++): compile a C99 caller
+    with -pedantic, link it against libmapc.so and run the calls that need no GPU."""
+    import subprocess
+    src = tmp_path / "caller.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <string.h>
+#include "mapc.h"
+int main(void) {
+    mapc_posvelo p; mapc_shared_handles h; mapc_compute *c = 0;
+    memset(&p, 0, sizeof p); memset(&h, 0, sizeof h);
+    if (sizeof(mapc_posvelo) != 32) return 2;
+    if (mapc_plan_segments(262144u) != 8 || mapc_plan_segments(10000u) != 32) return 3;
+    if (mapc_compute_create(&c, 0u, 0, 0) != MAPC_ERR_INVALID_ARGUMENT) return 4;
+    if (strstr(mapc_last_error(), "num_particles") == 0) return 5;
+    printf("%s\n", mapc_version());
+    return 0;
+}
+""")
+    exe = tmp_path / "caller"
+    lib_dir = os.path.dirname(mapc.LIB_PATH)
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(REPO_ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", lib_dir, "-lmapc", f"-Wl,-rpath,{lib_dir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out
+    assert "mapc" in out.stdout
