@@ -349,3 +349,40 @@ def test_batched_steps_equal_single_steps(mapc, gpu):
         c.WaitForGpu()
         assert c.Download().tobytes() == single.tobytes()
         assert c.GetSharedHandles().m_bufferIndex == 1      # 7 steps: odd number of flips
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 65, 129])
+def test_tiny_and_ragged_sizes(mapc, oracle, gpu, n):
+    """Edge sizes: a single body (self-pair only: exactly zero force), sizes straddling the 64-body tile."""
+    p = mapc.ic.uniform_sphere(n, 50.0, seed=100 + n, speed=3.0)
+    got = gpu_steps(mapc, p, 3)
+    ref = p
+    for _ in range(3):
+        ref = oracle.step_allpairs(ref, flavour=oracle.MIRRORED)
+    err = oracle.rel_errors(got, ref)
+    assert max(err.values()) <= 1e-5, err
+    if n == 1:
+        assert got["pos"][0, 3] == 0.0                      # no other body: |accel| is exactly 0
+        np.testing.assert_allclose(got["pos"][0, :3], p["pos"][0, :3] + 3 * 0.1 * p["velo"][0, :3], rtol=1e-6)
+
+
+def test_zero_and_one_active_particles(mapc, oracle, gpu):
+    """Simulate(0) dispatches nothing (Dispatch(0), Compute.cpp:1041) but still signals and flips;
+    Simulate(1) updates the first 64 bodies (one thread group) against a single source."""
+    n = 300
+    p = mapc.ic.uniform_sphere(n, 80.0, seed=9, speed=1.0)
+    with mapc.Compute(n, 0) as c:
+        c.Upload(p)
+        f = c.GetFenceValue()
+        c.Simulate(0, 0)
+        c.WaitForGpu()
+        assert c.GetFenceValue() == f + 2 and c.GetSharedHandles().m_bufferIndex == 1
+        assert c.Download().tobytes() == p.tobytes()        # the written side still holds the upload
+        c.Simulate(1, 0)
+        c.WaitForGpu()
+        got = c.Download()
+    ref = oracle.step_allpairs(p, n_active=1, out=p.copy(), flavour=oracle.MIRRORED)
+    assert oracle.num_targets(n, 1) == 64
+    err = oracle.rel_errors(got[:64], ref[:64])
+    assert max(err.values()) <= 1e-5, err
+    assert got[64:].tobytes() == p[64:].tobytes()

@@ -157,22 +157,25 @@ struct Timer {
 static int g_sms = 148;
 static double g_peak_tflops = 74.45;
 
+static int g_targets = 0;   // 0 = all bodies are targets; otherwise a shard of that many (multi-GPU shapes)
+
 template <int P, int T, int TJ, int U, int MINB, int ORDER = 0>
 void run_force(const float4 *pos, float4 *partial, int n, Timer &t)
 {
+    const int n_tgt = g_targets > 0 ? g_targets : n;
     const int S = 8;
     mapc::StepArgs args{};
     args.pos = pos;
     args.partial = partial;
     args.partial_stride = n;
     args.i_first = 0;
-    args.i_cnt = n;
+    args.i_cnt = n_tgt;
     args.n_sources = n;
     args.S = S;
     args.segs.count = S;
     for (int s = 0; s < S; ++s) args.segs.ids[s] = s;
     const int per_block = T * 2 * P;
-    args.n_iblocks = (n + per_block - 1) / per_block;
+    args.n_iblocks = (n_tgt + per_block - 1) / per_block;
     auto kernel = mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, false>;
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, T, 0));
@@ -181,7 +184,7 @@ void run_force(const float4 *pos, float4 *partial, int n, Timer &t)
     const long long cells = (long long)args.n_iblocks * S;
     const dim3 grid(args.n_iblocks, S);
     const float ms = t.best([&] { kernel<<<grid, T>>>(args); }, 4);
-    const double ginter = (double)n * n / (ms * 1e-3) / 1e9;
+    const double ginter = (double)n * n_tgt / (ms * 1e-3) / 1e9;
     printf("force %s P=%d T=%3d TJ=%3d U=%d minB=%2d regs=%3d occ=%2d blk/SM (%2d warps) cells=%5lld : %8.3f ms %8.1f G int/s %5.1f %% of %.2f TF\n",
            ORDER == 0 ? "pair-major" : (ORDER == 2 ? "op-major  " : "crossed-sc"), P, T, TJ, U, MINB, fa.numRegs, occ, occ * T / 32, cells, ms, ginter,
            100.0 * ginter * 20.0 / 1e3 / g_peak_tflops, g_peak_tflops);
@@ -190,6 +193,7 @@ void run_force(const float4 *pos, float4 *partial, int n, Timer &t)
 int main(int argc, char **argv)
 {
     const int n = argc > 1 ? atoi(argv[1]) : 262144;
+    g_targets = argc > 2 ? atoi(argv[2]) : 0;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     g_sms = prop.multiProcessorCount;
@@ -254,7 +258,7 @@ int main(int argc, char **argv)
     CK(cudaMalloc(&pos, sizeof(float4) * n));
     CK(cudaMalloc(&partial, sizeof(float4) * n * 8));
     CK(cudaMemcpy(pos, h.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
-    printf("--- force_segments_kernel, N = %d, S = 8 ---\n", n);
+    printf("--- force_cells_kernel, %d sources, %d targets, S = 8 ---\n", n, g_targets > 0 ? g_targets : n);
 #ifdef SWEEP_BROAD
     run_force<4, 256, 256, 1, 2, 0>(pos, partial, n, t);
     run_force<4, 256, 256, 1, 3, 0>(pos, partial, n, t);
@@ -403,8 +407,10 @@ int main(int argc, char **argv)
 #else
     run_force<4, 256, 256, 8, 2, 0>(pos, partial, n, t);
     run_force<4, 128, 256, 8, 4, 0>(pos, partial, n, t);
+    run_force<2, 256, 256, 8, 2, 0>(pos, partial, n, t);
     run_force<2, 128, 256, 4, 4, 2>(pos, partial, n, t);
     run_force<2, 64, 64, 4, 8, 2>(pos, partial, n, t);
+    run_force<2, 64, 64, 8, 8, 0>(pos, partial, n, t);
     run_force<1, 64, 64, 8, 16, 0>(pos, partial, n, t);
     run_force<1, 32, 64, 8, 32, 0>(pos, partial, n, t);
 #endif
