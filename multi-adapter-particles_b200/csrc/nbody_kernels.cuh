@@ -193,6 +193,33 @@ struct StepArgs {
     unsigned long long flag_expect;
 };
 
+// ---- 1-D TMA (cp.async.bulk) staging helpers: shared::cluster destination, mbarrier completion ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned long long *p)
 {
     unsigned long long v;
@@ -213,15 +240,27 @@ __device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned lo
 // PEER: the cell's sources are read straight from the owning GPU's memory (no all-gather): the block
 // first waits until the owner's step flag says its positions of this step are published.  Waiting
 // cannot deadlock: a peer's step k-1 never depends on this GPU's step k.
-template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER = false>
+// TMA: the source stages are filled by 1-D bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) issued
+// by one thread instead of LDG/STS by all; measured A/B in profiles/ -- it changes nothing, because
+// staging is ~0.02 % of the instruction stream either way.
+template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER = false, bool TMA = false>
 __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_constant__ StepArgs a)
 {
     constexpr int kLoads = TJ / T;  // staging loads per thread per stage
     static_assert(TJ % T == 0 && TJ % MAPC_BLOCK_SIZE == 0, "stage must be a multiple of block and tile size");
-    __shared__ float4 tile[2][TJ];
+    __shared__ __align__(128) float4 tile[2][TJ];
+    __shared__ __align__(8) unsigned long long full_bar[2];
     __shared__ int s_is_last;
 
     const int tid = threadIdx.x;
+    if (TMA) {
+        if (tid == 0) {
+            mbar_init(&full_bar[0], 1);
+            mbar_init(&full_bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     const float4 *__restrict__ pos = a.pos;
     const float4 *__restrict__ src = PEER ? a.seg_src[blockIdx.y] : a.pos;   // where this cell's sources live
     // Programmatic dependent launch (batched steps): let the next step's grid start filling SMs as this
@@ -263,22 +302,39 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
 
         const int n_stages = (j1 - j0 + TJ - 1) / TJ;
         float4 stage[kLoads];
-        if (n_stages > 0) {  // prologue: stage 0 -> smem buffer 0
-#pragma unroll
-            for (int l = 0; l < kLoads; ++l) {
-                const int j = j0 + l * T + tid;
-                stage[l] = j < j1 ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (TMA) {
+            if (n_stages > 0 && tid == 0) {
+                const unsigned bytes = (unsigned)(((j1 - j0) < TJ ? (j1 - j0) : TJ) * sizeof(float4));
+                mbar_expect_tx(&full_bar[0], bytes);
+                tma_load_1d(&tile[0][0], src + j0, bytes, &full_bar[0]);
             }
+        } else {
+            if (n_stages > 0) {  // prologue: stage 0 -> smem buffer 0
 #pragma unroll
-            for (int l = 0; l < kLoads; ++l) tile[0][l * T + tid] = stage[l];
+                for (int l = 0; l < kLoads; ++l) {
+                    const int j = j0 + l * T + tid;
+                    stage[l] = j < j1 ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int l = 0; l < kLoads; ++l) tile[0][l * T + tid] = stage[l];
+            }
+            __syncthreads();
         }
-        __syncthreads();
 
         for (int t = 0; t < n_stages; ++t) {
             const int buf = t & 1;
             const int jt = j0 + t * TJ;
             const bool has_next = (t + 1) < n_stages;
-            if (has_next) {  // prefetch the next stage into registers while this one is consumed
+            if (TMA) {
+                // the other buffer was released by the barrier that ended the previous iteration
+                if (has_next && tid == 0) {
+                    const int rest = j1 - (jt + TJ);
+                    const unsigned bytes = (unsigned)((rest < TJ ? rest : TJ) * sizeof(float4));
+                    mbar_expect_tx(&full_bar[buf ^ 1], bytes);
+                    tma_load_1d(&tile[buf ^ 1][0], src + jt + TJ, bytes, &full_bar[buf ^ 1]);
+                }
+                mbar_wait(&full_bar[buf], (unsigned)((t >> 1) & 1));
+            } else if (has_next) {  // prefetch the next stage into registers while this one is consumed
 #pragma unroll
                 for (int l = 0; l < kLoads; ++l) {
                     const int j = jt + TJ + l * T + tid;
@@ -309,7 +365,7 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                 for (int p = 0; p < P; ++p)
                     pair_interaction<(ORDER == 3 ? 2 : 0)>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
             }
-            if (has_next) {
+            if (!TMA && has_next) {
 #pragma unroll
                 for (int l = 0; l < kLoads; ++l) tile[buf ^ 1][l * T + tid] = stage[l];
             }
