@@ -380,6 +380,11 @@ struct mapc_compute {
     cudaEvent_t t_begin[kTimerSlots] = {}, t_end[kTimerSlots] = {};
     bool t_pending[kTimerSlots] = {};
     int t_steps[kTimerSlots] = {};   // steps covered by the slot's event pair (batched Simulate)
+    bool t_stamped[kTimerSlots] = {};          // slot timed by in-kernel %globaltimer stamps, not events
+    uint64_t t_fence_value[kTimerSlots] = {};  // fence value signalled after the slot's step(s)
+    unsigned long long *stamps = nullptr;      // pinned host: [slot][begin, end] in ns
+    unsigned *done = nullptr;                  // device: target blocks integrated this step
+    unsigned long long *stamp_begin_next = nullptr, *stamp_end_next = nullptr;  // for the next force launch(es)
     uint64_t t_next = 0, t_resolved = 0;
     float ms_average = 0.f, ms_last = 0.f;
     std::vector<float> step_log;  // raw samples not yet handed out by mapc_compute_step_times
@@ -396,10 +401,23 @@ void resolve_timers(mapc_compute *c, bool block)
     while (c->t_resolved < c->t_next) {
         const int slot = (int)(c->t_resolved % mapc_compute::kTimerSlots);
         if (c->t_pending[slot]) {
-            if (block) cudaEventSynchronize(c->t_end[slot]);
-            else if (cudaEventQuery(c->t_end[slot]) != cudaSuccess) return;
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, c->t_begin[slot], c->t_end[slot]) == cudaSuccess) {
+            bool have = false;
+            if (c->t_stamped[slot]) {
+                // in-kernel stamps: valid once the fence value signalled after the step has completed
+                if (mapc_fence_completed_value(c->fence) < c->t_fence_value[slot]) {
+                    if (!block) return;
+                    if (mapc_fence_wait_host(c->fence, c->t_fence_value[slot], 60000) != MAPC_OK) return;
+                }
+                const unsigned long long t0 = c->stamps[2 * slot], t1 = c->stamps[2 * slot + 1];
+                have = t1 > t0 && t0 != 0;
+                ms = have ? (float)((double)(t1 - t0) * 1e-6) : 0.f;
+            } else {
+                if (block) cudaEventSynchronize(c->t_end[slot]);
+                else if (cudaEventQuery(c->t_end[slot]) != cudaSuccess) return;
+                have = cudaEventElapsedTime(&ms, c->t_begin[slot], c->t_end[slot]) == cudaSuccess;
+            }
+            if (have) {
                 if (c->t_steps[slot] > 1) ms /= (float)c->t_steps[slot];   // per-step average of a batch
                 // D3D12GpuTimer.h:151-153: t = (t*(N-1) + delta)/N
                 c->ms_average = (c->ms_average * (mapc_compute::kAverageOver - 1.f) + ms) /
@@ -513,7 +531,7 @@ mapc_status create_common(mapc_compute **out, uint32_t n, int device, int rank, 
         c->gcompute.device = device;
         MAPC_CUDA(cudaStreamCreateWithFlags(&c->comm, cudaStreamNonBlocking));
         MAPC_CUDA(cudaStreamCreateWithFlags(&c->compute2, cudaStreamNonBlocking));
-        MAPC_CUDA(cudaEventCreateWithFlags(&c->ev_step_begin, cudaEventDisableTiming));
+        MAPC_CUDA(cudaEventCreate(&c->ev_step_begin));   // timing-enabled: mapc_compute_exchange_times
         MAPC_CUDA(cudaEventCreateWithFlags(&c->ev_remote_done, cudaEventDisableTiming));
         for (int s = 0; s < 2; ++s) {
             MAPC_CUDA(cudaMalloc(&c->posvelo[s], (size_t)c->n_local * sizeof(mapc_posvelo)));
@@ -527,6 +545,11 @@ mapc_status create_common(mapc_compute **out, uint32_t n, int device, int rank, 
             MAPC_CUDA(cudaEventCreate(&c->t_end[k]));
         }
         MAPC_TRY(ensure_partial(c, mapc_plan_segments(n)));
+        MAPC_CUDA(cudaHostAlloc((void **)&c->stamps, 2 * mapc_compute::kTimerSlots * sizeof(unsigned long long),
+                                cudaHostAllocPortable | cudaHostAllocMapped));
+        memset(c->stamps, 0, 2 * mapc_compute::kTimerSlots * sizeof(unsigned long long));
+        MAPC_CUDA(cudaMalloc(&c->done, 64));
+        MAPC_CUDA(cudaMemset(c->done, 0, 64));
         MAPC_CUDA(cudaMalloc(&c->counters, ((size_t)c->n_local / 64 + 2) * sizeof(unsigned)));
         MAPC_CUDA(cudaMemset(c->counters, 0, ((size_t)c->n_local / 64 + 2) * sizeof(unsigned)));
         // Compute.cpp:434-436: fence created with value 0, m_fenceValue++ -> 1
@@ -716,6 +739,8 @@ mapc_status mapc_compute_destroy(mapc_compute *c)
     }
     if (c->partial) cudaFree(c->partial);
     if (c->counters) cudaFree(c->counters);
+    if (c->done) cudaFree(c->done);
+    if (c->stamps) cudaFreeHost(c->stamps);
     if (c->upload_stage) cudaFree(c->upload_stage);
     if (c->ev_integrated) cudaEventDestroy(c->ev_integrated);
     for (int k = 0; k < mapc_compute::kTimerSlots; ++k) {
@@ -804,22 +829,39 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
 
 // `steps` consecutive steps (ping-pong starting with write side b0) inside ONE timer pair.
 static mapc_status enqueue_steps(mapc_compute *c, uint32_t b0, int n_targets, int n_sources, float delta_time,
-                                 float damping, mapc_force_mode mode, int steps)
+                                 float damping, mapc_force_mode mode, int steps, uint64_t fence_value_after)
 {
+    const bool timers = env_int("MAPC_TIMERS", 1) != 0;   // experiment switch
     resolve_timers(c, false);
     const int slot = (int)(c->t_next % mapc_compute::kTimerSlots);
     if (c->t_pending[slot]) resolve_timers(c, true);
-    MAPC_CUDA(cudaEventRecord(c->t_begin[slot], c->compute));  // BeginTimer, Compute.cpp:1020
+    // Two timing-enabled event records cost ~8 us of stream time per step on B200 (measured at
+    // N = 10,000), so the fused all-pairs kernel stamps %globaltimer itself; the event pair remains for
+    // the well kernel and the unfused path.
+    const bool stamped = timers && mode == MAPC_FORCE_ALLPAIRS && n_targets > 0 && env_int("MAPC_FUSE", 1) != 0 &&
+                         env_int("MAPC_TIMER_EVENTS", 0) == 0;
+    if (stamped) {
+        c->stamps[2 * slot] = 0;
+        c->stamps[2 * slot + 1] = 0;
+    } else if (timers) {
+        MAPC_CUDA(cudaEventRecord(c->t_begin[slot], c->compute));  // BeginTimer, Compute.cpp:1020
+    }
     const bool pdl = steps > 1 && c->world == 1 && mode == MAPC_FORCE_ALLPAIRS && env_int("MAPC_FUSE", 1) != 0 &&
                      env_int("MAPC_PDL", 1) != 0;
     for (int k = 0; k < steps; ++k) {
         c->pdl_next = pdl && k > 0;
+        c->stamp_begin_next = (stamped && k == 0) ? &c->stamps[2 * slot] : nullptr;
+        c->stamp_end_next = (stamped && k == steps - 1) ? &c->stamps[2 * slot + 1] : nullptr;
         const mapc_status st = enqueue_one(c, (b0 + (uint32_t)k) & 1u, n_targets, n_sources, delta_time, damping, mode);
         c->pdl_next = false;
+        c->stamp_begin_next = c->stamp_end_next = nullptr;
         if (st != MAPC_OK) return st;
     }
-    MAPC_CUDA(cudaEventRecord(c->t_end[slot], c->compute));  // EndTimer, Compute.cpp:1046
+    if (!timers) return MAPC_OK;
+    if (!stamped) MAPC_CUDA(cudaEventRecord(c->t_end[slot], c->compute));  // EndTimer, Compute.cpp:1046
     c->t_pending[slot] = true;
+    c->t_stamped[slot] = stamped;
+    c->t_fence_value[slot] = fence_value_after;
     c->t_steps[slot] = steps;
     ++c->t_next;
     return MAPC_OK;
@@ -863,6 +905,9 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             args.pos_next = c->packed[b];
             args.dt = delta_time;
             args.damping = damping;
+            args.done = c->done;
+            args.stamp_begin = c->stamp_begin_next;   // consumed by the first launch of the step
+            args.stamp_end = c->stamp_end_next;       // every launch: whichever finishes the step writes it
             mapc::SegList local{0, {}}, remote{0, {}};
             int owner[MAPC_MAX_SEGMENTS];
             bool peer = c->peer_mode && fuse && n_sources == (int)c->n && env_int("MAPC_PEER", 1) != 0;
@@ -889,6 +934,7 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             args.segs = local;
             MAPC_TRY(fuse ? launch_force_shape<true>(c, pl, args, c->compute)
                           : launch_force_shape<false>(c, pl, args, c->compute));
+            if (local.count > 0) args.stamp_begin = nullptr;
             if (remote.count > 0) {
                 MAPC_CUDA(cudaStreamWaitEvent(c->compute2, c->ev_step_begin, 0));
                 args.segs = remote;
@@ -966,8 +1012,9 @@ mapc_status mapc_compute_simulate_steps(mapc_compute *c, int num_active_particle
     const int n_targets = local_targets(c, num_active_particles);
     const int n_sources = num_active_particles;
     const mapc_force_mode mode = c->mode;
+    const uint64_t fence_value_after = c->fence_value + (uint64_t)(steps - 1);
     MAPC_TRY(mapc::gs_call(&c->gcompute, [=]() -> mapc_status {
-        return enqueue_steps(c, b, n_targets, n_sources, delta_time, damping, mode, steps);
+        return enqueue_steps(c, b, n_targets, n_sources, delta_time, damping, mode, steps, fence_value_after);
     }));
 
     // MoveToNextFrame, Compute.cpp:993-1004 (a batch consumes one fence value per step and signals the last)
@@ -1104,9 +1151,9 @@ mapc_status mapc_compute_exchange_times(mapc_compute *c, float *gather_ms, float
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev_gather_begin[side], c->ev_gathered[side]) == cudaSuccess && gather_ms)
         *gather_ms = ms;
-    const int slot = (int)((c->t_next - 1) % mapc_compute::kTimerSlots);
-    if (cudaEventQuery(c->t_end[slot]) == cudaSuccess &&
-        cudaEventElapsedTime(&ms, c->t_begin[slot], c->ev_gathered[side]) == cudaSuccess && tail_past_step_begin_ms)
+    // ev_step_begin: recorded on the compute stream when the consuming (= last) step began
+    if (cudaEventQuery(c->ev_step_begin) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, c->ev_step_begin, c->ev_gathered[side]) == cudaSuccess && tail_past_step_begin_ms)
         *tail_past_step_begin_ms = ms;   // > 0: the gather was still running this long into the consuming step
     return MAPC_OK;
 }

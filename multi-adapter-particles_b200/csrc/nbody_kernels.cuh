@@ -191,7 +191,20 @@ struct StepArgs {
     const float4 *seg_src[MAPC_MAX_SEGMENTS];
     const unsigned long long *seg_flag[MAPC_MAX_SEGMENTS];
     unsigned long long flag_expect;
+    // "simulate ms" timer without stream operations (the reference brackets its Dispatch with in-queue
+    // timestamp queries, D3D12GpuTimer.h:117-129): block (0,0) stamps %globaltimer when it starts, the
+    // block that integrates the LAST target block of the step stamps it when it is done
+    unsigned long long *stamp_begin;   // pinned host memory, or null
+    unsigned long long *stamp_end;     // pinned host memory, or null
+    unsigned *done;                    // target blocks integrated so far this step (device)
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ---- 1-D TMA (cp.async.bulk) staging helpers: shared::cluster destination, mbarrier completion ----
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -268,6 +281,8 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
     // Both are no-ops for a launch without the programmatic-serialization attribute.
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (FUSE && a.stamp_begin != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
+        *a.stamp_begin = global_timer_ns();
     if (PEER) {
         const unsigned long long *flag = a.seg_flag[blockIdx.y];
         if (flag != nullptr) {
@@ -415,6 +430,15 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                     }
                 }
                 if (tid == 0) a.counters[ib] = 0u;  // ready for the next step
+                if (a.stamp_end != nullptr) {
+                    __syncthreads();                 // every thread's integrate stores are issued
+                    if (tid == 0 && atomicAdd(a.done, 1u) + 1u == (unsigned)a.n_iblocks) {
+                        *a.done = 0u;                // the step is complete: this was its last target block
+                        __threadfence();
+                        *a.stamp_end = global_timer_ns();
+                        __threadfence_system();
+                    }
+                }
             }
         }
     }

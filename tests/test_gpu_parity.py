@@ -265,6 +265,16 @@ def test_gpu_timer_and_launch_counter(mapc, gpu):
         assert c.KernelLaunches() == before + 8       # one fused force+integrate kernel per step
         times, last_ms = c.GetGpuTimes()
         assert times[0][1] == "simulate ms" and times[0][0] > 0 and last_ms > 0
+        stamped = float(np.median(c.StepTimes()))      # in-kernel %globaltimer stamps (default)
+        try:
+            os.environ["MAPC_TIMER_EVENTS"] = "1"       # the same timer through cudaEvent pairs
+            for _ in range(8):
+                c.Simulate(n, 0)
+            c.WaitForGpu()
+            events = float(np.median(c.StepTimes()))
+        finally:
+            os.environ.pop("MAPC_TIMER_EVENTS", None)
+        assert abs(stamped - events) <= 0.15 * events + 0.004, (stamped, events)
 
 
 def test_init_particles_two_shells(mapc, gpu):
