@@ -396,3 +396,30 @@ def test_zero_and_one_active_particles(mapc, oracle, gpu):
     err = oracle.rel_errors(got[:64], ref[:64])
     assert max(err.values()) <= 1e-5, err
     assert got[64:].tobytes() == p[64:].tobytes()
+
+
+def test_allpairs_ten_steps_65536_lattice(mapc, oracle, gpu):
+    """Ten steps at a mid size against the LITERAL oracle (well-conditioned lattice IC), 1e-4."""
+    n = 65_536
+    p = mapc.ic.lattice_sphere(n, 4000.0, seed=6, speed=1.0)
+    got = gpu_steps(mapc, p, 10)
+    ref = p
+    for _ in range(10):
+        ref = oracle.step_allpairs(ref, flavour=oracle.LITERAL)
+    assert_close(oracle, got, ref, TOL_10, "10 steps, N=65,536 lattice")
+
+
+@pytest.mark.parametrize("name,n", [("sphere_1048576", 1_048_576), ("plummer_4194304", 4_194_304)])
+def test_baseline_configs_4_and_5_subsampled_parity(mapc, oracle, gpu, name, n):
+    """BASELINE configs 4 and 5 at their full sizes on one GPU: one step, oracle on 2048 random targets
+    against all N sources (same canonical order), plus momentum cancellation over all bodies."""
+    p = mapc.ic.workload(name)
+    assert p.shape[0] == n
+    got = gpu_steps(mapc, p, 1)
+    rng = np.random.default_rng(7)
+    idx = np.sort(rng.choice(n, 2048, replace=False)).astype(np.int32)
+    ref = oracle.step_allpairs_targets(p, idx, flavour=oracle.LITERAL)
+    err = oracle.rel_errors(got[idx], ref)
+    assert max(err.values()) <= TOL_1, err
+    dv = got["velo"][:, :3].astype(np.float64) - p["velo"][:, :3].astype(np.float64)   # = accel * dt
+    assert np.all(np.abs(dv.sum(axis=0)) < 1e-4 * np.abs(dv).sum(axis=0))
