@@ -158,13 +158,14 @@ struct Timer {
 static int g_sms = 148;
 static double g_peak_tflops = 74.45;
 
+static int g_segments = 8;  // canonical S (argv[3])
 static int g_targets = 0;   // 0 = all bodies are targets; otherwise a shard of that many (multi-GPU shapes)
 
 template <int P, int T, int TJ, int U, int MINB, int ORDER = 0, bool TMA = false>
 void run_force(const float4 *pos, float4 *partial, int n, Timer &t)
 {
     const int n_tgt = g_targets > 0 ? g_targets : n;
-    const int S = 8;
+    const int S = g_segments;
     mapc::StepArgs args{};
     args.pos = pos;
     args.partial = partial;
@@ -187,7 +188,7 @@ void run_force(const float4 *pos, float4 *partial, int n, Timer &t)
     const float ms = t.best([&] { kernel<<<grid, T>>>(args); }, 4);
     const double ginter = (double)n * n_tgt / (ms * 1e-3) / 1e9;
     printf("force %s %s P=%d T=%3d TJ=%3d U=%d minB=%2d regs=%3d occ=%2d blk/SM (%2d warps) cells=%5lld : %8.3f ms %8.1f G int/s %5.1f %% of %.2f TF\n",
-           TMA ? "tma-stage" : "ldg-stage", ORDER == 0 ? "pair-major" : (ORDER == 2 ? "op-major  " : "crossed-sc"), P, T, TJ, U, MINB, fa.numRegs, occ, occ * T / 32, cells, ms, ginter,
+           TMA ? "tma-stage" : "ldg-stage", ORDER == 0 ? "pair-major" : (ORDER == 2 ? "op-major  " : (ORDER == 4 ? "mass-hoist" : "crossed-sc")), P, T, TJ, U, MINB, fa.numRegs, occ, occ * T / 32, cells, ms, ginter,
            100.0 * ginter * 20.0 / 1e3 / g_peak_tflops, g_peak_tflops);
 }
 
@@ -195,6 +196,7 @@ int main(int argc, char **argv)
 {
     const int n = argc > 1 ? atoi(argv[1]) : 262144;
     g_targets = argc > 2 ? atoi(argv[2]) : 0;
+    g_segments = argc > 3 ? atoi(argv[3]) : 8;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     g_sms = prop.multiProcessorCount;
@@ -257,9 +259,25 @@ int main(int argc, char **argv)
     for (auto &v : h) v = make_float4(8000.f * (rnd() - 0.5f), 8000.f * (rnd() - 0.5f), 8000.f * (rnd() - 0.5f), 0.f);
     float4 *pos, *partial;
     CK(cudaMalloc(&pos, sizeof(float4) * n));
-    CK(cudaMalloc(&partial, sizeof(float4) * n * 8));
+    CK(cudaMalloc(&partial, sizeof(float4) * n * 64));
     CK(cudaMemcpy(pos, h.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
     printf("--- force_cells_kernel, %d sources, %d targets, S = 8 ---\n", n, g_targets > 0 ? g_targets : n);
+#ifdef SWEEP_SMALL
+    run_force<1, 64, 64, 8, 16, 0>(pos, partial, n, t);
+    run_force<1, 64, 64, 8, 18, 0>(pos, partial, n, t);
+    run_force<1, 64, 64, 8, 20, 0>(pos, partial, n, t);
+    run_force<1, 64, 64, 4, 20, 0>(pos, partial, n, t);
+    run_force<1, 32, 64, 8, 32, 0>(pos, partial, n, t);
+    run_force<2, 64, 64, 4, 8, 2>(pos, partial, n, t);
+    run_force<2, 64, 64, 4, 10, 2>(pos, partial, n, t);
+    run_force<2, 32, 64, 4, 16, 2>(pos, partial, n, t);
+    run_force<2, 32, 64, 4, 20, 2>(pos, partial, n, t);
+    run_force<2, 32, 64, 8, 20, 0>(pos, partial, n, t);
+    run_force<1, 128, 256, 8, 8, 0>(pos, partial, n, t);
+    run_force<1, 128, 256, 8, 10, 0>(pos, partial, n, t);
+    run_force<2, 128, 256, 4, 4, 2>(pos, partial, n, t);
+    return 0;
+#endif
 #ifdef SWEEP_BROAD
     run_force<4, 256, 256, 1, 2, 0>(pos, partial, n, t);
     run_force<4, 256, 256, 1, 3, 0>(pos, partial, n, t);
@@ -414,6 +432,9 @@ int main(int argc, char **argv)
     run_force<2, 64, 64, 8, 8, 0>(pos, partial, n, t);
     run_force<1, 64, 64, 8, 16, 0>(pos, partial, n, t);
     run_force<1, 32, 64, 8, 32, 0>(pos, partial, n, t);
+    run_force<4, 256, 256, 8, 2, 4>(pos, partial, n, t);   // experiment: x mass hoisted (11 lane-ops)
+    run_force<4, 128, 256, 8, 4, 4>(pos, partial, n, t);
+    run_force<2, 128, 256, 4, 4, 4>(pos, partial, n, t);
     run_force<4, 256, 256, 8, 2, 0, true>(pos, partial, n, t);
     run_force<4, 128, 256, 8, 4, 0, true>(pos, partial, n, t);
     run_force<2, 128, 256, 4, 4, 2, true>(pos, partial, n, t);
