@@ -257,7 +257,8 @@ MAPC_API mapc_status mapc_consumer_counters(const mapc_consumer *r, uint64_t out
 MAPC_API mapc_status mapc_consumer_wait_for_gpu(mapc_consumer *r);
 
 /* ---- plan / diagnostics -------------------------------------------------------------------- */
-/* canonical number of j segments for n sources: 8 when n >= 131072 else 32.  The partial sums
+/* canonical number of j segments for n sources: 32 below 131072 sources; from there 8, doubling up to
+ * 64 so that no segment exceeds 65,536 sources (bounds the fp32 accumulation error).  The partial sums
  * of the segments are combined left to right, independent of the GPU count. */
 MAPC_API int mapc_plan_segments(uint32_t n_sources);
 /* number of this library's kernels launched by the handle so far */

@@ -433,7 +433,7 @@ void resolve_timers(mapc_compute *c, bool block)
 }
 
 // grid = (target blocks, segments of this launch): one cell per thread block
-template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER>
+template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER, bool INLOOP>
 mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream_t stream)
 {
     dim3 grid((unsigned)args.n_iblocks, (unsigned)args.segs.count, 1);
@@ -450,25 +450,25 @@ mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        MAPC_CUDA(cudaLaunchKernelEx(&cfg, mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER>, args));
+        MAPC_CUDA(cudaLaunchKernelEx(&cfg, mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER, false, INLOOP>, args));
     } else {
-        mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER><<<grid, T, 0, stream>>>(args);
+        mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER, false, INLOOP><<<grid, T, 0, stream>>>(args);
     }
     MAPC_CUDA(cudaGetLastError());
     ++c->launches;
     return MAPC_OK;
 }
 
-template <bool FUSE, bool PEER = false>
+template <bool FUSE, bool PEER = false, bool INLOOP = false>
 mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::StepArgs &args, cudaStream_t stream)
 {
     if (args.segs.count == 0 || args.i_cnt <= 0) return MAPC_OK;
-    if (pl.pairs == 4 && pl.threads == 256) return launch_force<4, 256, 256, 8, 2, 0, FUSE, PEER>(c, args, stream);
-    if (pl.pairs == 4 && pl.threads == 128) return launch_force<4, 128, 256, 8, 4, 0, FUSE, PEER>(c, args, stream);
-    if (pl.pairs == 2 && pl.threads == 128) return launch_force<2, 128, 256, 4, 4, 2, FUSE, PEER>(c, args, stream);
-    if (pl.pairs == 2 && pl.threads == 64) return launch_force<2, 64, 64, 4, 8, 2, FUSE, PEER>(c, args, stream);
-    if (pl.pairs == 1 && pl.threads == 64) return launch_force<1, 64, 64, 8, 16, 0, FUSE, PEER>(c, args, stream);
-    return launch_force<1, 32, 64, 8, 32, 0, FUSE, PEER>(c, args, stream);
+    if (pl.pairs == 4 && pl.threads == 256) return launch_force<4, 256, 256, 8, 2, 0, FUSE, PEER, INLOOP>(c, args, stream);
+    if (pl.pairs == 4 && pl.threads == 128) return launch_force<4, 128, 256, 8, 4, 0, FUSE, PEER, INLOOP>(c, args, stream);
+    if (pl.pairs == 2 && pl.threads == 128) return launch_force<2, 128, 256, 4, 4, 2, FUSE, PEER, INLOOP>(c, args, stream);
+    if (pl.pairs == 2 && pl.threads == 64) return launch_force<2, 64, 64, 4, 8, 2, FUSE, PEER, INLOOP>(c, args, stream);
+    if (pl.pairs == 1 && pl.threads == 64) return launch_force<1, 64, 64, 8, 16, 0, FUSE, PEER, INLOOP>(c, args, stream);
+    return launch_force<1, 32, 64, 8, 32, 0, FUSE, PEER, INLOOP>(c, args, stream);
 }
 
 // targets of this shard that a Simulate(n_active) updates, as a count from i_first
@@ -592,7 +592,18 @@ mapc_status mapc_device_count(int *count)
     return MAPC_OK;
 }
 
-int mapc_plan_segments(uint32_t n_sources) { return n_sources >= 131072u ? 8 : 32; }
+// Canonical segment count: a function of the number of sources only (never of the GPU count or the
+// launch shape).  Small problems get 32 segments for parallelism; large ones keep every segment's
+// fp32 accumulation chain at <= 65,536 terms (8 segments up to 524,288 sources, then 16, 32, 64):
+// a sequential fp32 sum of 524,288 terms is ~1e-5 away from the fp64 sum -- the size of the parity
+// tolerance itself -- while 65,536-term chains stay near 1e-6.
+int mapc_plan_segments(uint32_t n_sources)
+{
+    if (n_sources < 131072u) return 32;
+    int s = 8;
+    while (s < MAPC_MAX_SEGMENTS && (uint64_t)s * 65536u < n_sources) s *= 2;
+    return s;
+}
 
 // ---- fences ------------------------------------------------------------------------------------
 mapc_status mapc_fence_create(mapc_fence **out, uint64_t initial_value)
@@ -910,7 +921,8 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             args.stamp_end = c->stamp_end_next;       // every launch: whichever finishes the step writes it
             mapc::SegList local{0, {}}, remote{0, {}};
             int owner[MAPC_MAX_SEGMENTS];
-            bool peer = c->peer_mode && fuse && n_sources == (int)c->n && env_int("MAPC_PEER", 1) != 0;
+            bool peer = c->peer_mode && fuse && n_sources == (int)c->n && env_int("MAPC_PEER", 1) != 0 &&
+                        env_int("MAPC_MASS_IN_LOOP", 0) == 0;
             for (int s = 0; s < pl.segments; ++s) {
                 int j0, j1;
                 mapc::segment_range(n_sources, pl.segments, s, j0, j1);
@@ -931,9 +943,15 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             // balances them (a lone local launch of few, long cells would leave most SMs idle).  The
             // arrival counters make the fused combine+integrate independent of which grid finishes last.
             if (remote.count > 0) MAPC_CUDA(cudaEventRecord(c->ev_step_begin, c->compute));
+            // MAPC_MASS_IN_LOOP=1: the shader's per-pair `mass * invDistCube` (12 lane-ops) instead of the
+            // default once-per-partial scale (11): A/B switch, fused non-peer path only
+            const bool inloop = fuse && env_int("MAPC_MASS_IN_LOOP", 0) != 0;
+            auto launch = [&](cudaStream_t st) -> mapc_status {
+                if (inloop) return launch_force_shape<true, false, true>(c, pl, args, st);
+                return fuse ? launch_force_shape<true>(c, pl, args, st) : launch_force_shape<false>(c, pl, args, st);
+            };
             args.segs = local;
-            MAPC_TRY(fuse ? launch_force_shape<true>(c, pl, args, c->compute)
-                          : launch_force_shape<false>(c, pl, args, c->compute));
+            MAPC_TRY(launch(c->compute));
             if (local.count > 0) args.stamp_begin = nullptr;
             if (remote.count > 0) {
                 MAPC_CUDA(cudaStreamWaitEvent(c->compute2, c->ev_step_begin, 0));
@@ -949,8 +967,7 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
                     MAPC_TRY((launch_force_shape<true, true>(c, pl, args, c->compute2)));
                 } else {
                     MAPC_CUDA(cudaStreamWaitEvent(c->compute2, c->ev_gathered[r], 0));
-                    MAPC_TRY(fuse ? launch_force_shape<true>(c, pl, args, c->compute2)
-                                  : launch_force_shape<false>(c, pl, args, c->compute2));
+                    MAPC_TRY(launch(c->compute2));
                 }
                 MAPC_CUDA(cudaEventRecord(c->ev_remote_done, c->compute2));
                 MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_remote_done, 0));

@@ -59,15 +59,14 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 //   distSqr = dot(r,r) + 25          (:48-49) 3 FFMA2, softening folded into the first
 //   invDist = rsqrt(distSqr)         (:51)   MUFU.RSQ x2
 //   invDistCube = (inv*inv)*inv      (:52)   2 FMUL2
-//   s = mass * invDistCube [* 1]     (:54)   FMUL2 (particles == 1 is an exact no-op)
+//   s = mass * invDistCube [* 1]     (:54)   FMUL2 (particles == 1 is an exact no-op)   [MASS_IN_LOOP]
 //   ai += r * s                      (:56)   3 FFMA2
-//
-// SCALAR_ACC: the three accumulations read three distinct register pairs each (r, s, ai).  The
-// register file feeds a packed FFMA2 only two fresh pairs per issue (measured: 3 cycles instead of
-// 2 when all three differ, tools/ubench), while scalar FFMA runs 3-operand at full rate -- so the
-// accumulations are issued as six scalar FFMAs on the halves of the same registers.  Same IEEE
-// fma per lane either way: the bits do not change.
-template <int SCALAR_ACC>
+// MASS_IN_LOOP = false (default): the uniform factor g_fParticleMass is left out of the pair and
+// applied once to each segment partial instead (lever (i)): 11 instead of 12
+// FMA-pipe lane-ops per interaction, 76 % instead of 72 % of the FP32 peak.  Same formula; each term
+// loses one rounding, so results differ from the per-pair multiply by ~1 ulp per partial -- far inside
+// the 1e-5 tolerance; the oracle's MIRRORED flavour does the same, LITERAL keeps the shader's order.
+template <bool MASS_IN_LOOP>
 __device__ __forceinline__ void pair_interaction(const float4 b, const float2 nxi, const float2 nyi,
                                                  const float2 nzi, float2 &ax, float2 &ay, float2 &az)
 {
@@ -82,37 +81,17 @@ __device__ __forceinline__ void pair_interaction(const float4 b, const float2 nx
     inv.y = rsqrt_approx(d2.y);
     const float2 inv2 = __fmul2_rn(inv, inv);
     const float2 inv3 = __fmul2_rn(inv2, inv);
-    // SCALAR_ACC == 3 (tools/ubench only): leave the uniform mass out of the loop -- 11 instead of 12
-    // lane-ops per interaction; the caller scales the sum once.  Changes rounding, never used by the library.
-    const float2 s = SCALAR_ACC == 3 ? inv3 : __fmul2_rn(inv3, make_float2(MAPC_PARTICLE_MASS, MAPC_PARTICLE_MASS));
-    if (SCALAR_ACC == 2) {
-        // crossed halves: the accumulator pair holds {target b, target a}, so each scalar FFMA reads two
-        // registers of one parity and one of the other (no three-way register-bank conflict)
-        ax.y = __fmaf_rn(dx.x, s.x, ax.y);
-        ax.x = __fmaf_rn(dx.y, s.y, ax.x);
-        ay.y = __fmaf_rn(dy.x, s.x, ay.y);
-        ay.x = __fmaf_rn(dy.y, s.y, ay.x);
-        az.y = __fmaf_rn(dz.x, s.x, az.y);
-        az.x = __fmaf_rn(dz.y, s.y, az.x);
-    } else if (SCALAR_ACC == 1) {
-        ax.x = __fmaf_rn(dx.x, s.x, ax.x);
-        ax.y = __fmaf_rn(dx.y, s.y, ax.y);
-        ay.x = __fmaf_rn(dy.x, s.x, ay.x);
-        ay.y = __fmaf_rn(dy.y, s.y, ay.y);
-        az.x = __fmaf_rn(dz.x, s.x, az.x);
-        az.y = __fmaf_rn(dz.y, s.y, az.y);
-    } else {
-        ax = __ffma2_rn(dx, s, ax);
-        ay = __ffma2_rn(dy, s, ay);
-        az = __ffma2_rn(dz, s, az);
-    }
+    const float2 s = MASS_IN_LOOP ? __fmul2_rn(inv3, make_float2(MAPC_PARTICLE_MASS, MAPC_PARTICLE_MASS)) : inv3;
+    ax = __ffma2_rn(dx, s, ax);
+    ay = __ffma2_rn(dy, s, ay);
+    az = __ffma2_rn(dz, s, az);
 }
 
 // The same arithmetic for all P pairs of a thread against one source body, written operation-major
 // (every step looped over the pairs) so neighbouring instructions share operands: the broadcast
 // source coordinate across the subtractions and the scale s across the three accumulations, which is
 // what lets the register-reuse cache feed the 3-operand FFMA2s.  Rounding is untouched.
-template <int P>
+template <int P, bool MASS_IN_LOOP>
 __device__ __forceinline__ void group_interaction(const float4 b, const float2 *nxi, const float2 *nyi,
                                                   const float2 *nzi, float2 *ax, float2 *ay, float2 *az)
 {
@@ -139,8 +118,10 @@ __device__ __forceinline__ void group_interaction(const float4 b, const float2 *
     for (int p = 0; p < P; ++p) s[p] = __fmul2_rn(d2[p], d2[p]);
 #pragma unroll
     for (int p = 0; p < P; ++p) s[p] = __fmul2_rn(s[p], d2[p]);
+    if (MASS_IN_LOOP) {
 #pragma unroll
-    for (int p = 0; p < P; ++p) s[p] = __fmul2_rn(s[p], make_float2(MAPC_PARTICLE_MASS, MAPC_PARTICLE_MASS));
+        for (int p = 0; p < P; ++p) s[p] = __fmul2_rn(s[p], make_float2(MAPC_PARTICLE_MASS, MAPC_PARTICLE_MASS));
+    }
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         ax[p] = __ffma2_rn(dx[p], s[p], ax[p]);
@@ -258,7 +239,8 @@ __device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned lo
 // TMA: the source stages are filled by 1-D bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) issued
 // by one thread instead of LDG/STS by all; measured A/B in profiles/ -- it changes nothing, because
 // staging is ~0.02 % of the instruction stream either way.
-template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER = false, bool TMA = false>
+template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER = false, bool TMA = false,
+          bool MASS_IN_LOOP = false>
 __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_constant__ StepArgs a)
 {
     constexpr int kLoads = TJ / T;  // staging loads per thread per stage
@@ -366,11 +348,11 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                 for (int j = 0; j < MAPC_BLOCK_SIZE; ++j) {
                     const float4 b = tile[buf][jb + j];
                     if (ORDER == 2) {
-                        group_interaction<P>(b, nxi, nyi, nzi, ax, ay, az);
+                        group_interaction<P, MASS_IN_LOOP>(b, nxi, nyi, nzi, ax, ay, az);
                     } else {
 #pragma unroll
                         for (int p = 0; p < P; ++p)
-                            pair_interaction<(ORDER == 3 ? 2 : (ORDER == 4 ? 3 : 0))>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+                            pair_interaction<MASS_IN_LOOP>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
                     }
                 }
             }
@@ -380,7 +362,7 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                 const float4 b = tile[buf][j];
 #pragma unroll
                 for (int p = 0; p < P; ++p)
-                    pair_interaction<(ORDER == 3 ? 2 : (ORDER == 4 ? 3 : 0))>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+                    pair_interaction<MASS_IN_LOOP>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
             }
             if (!TMA && has_next) {
 #pragma unroll
@@ -394,13 +376,14 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
         for (int p = 0; p < P; ++p) {
             const int ia = i_block + (2 * p) * T + tid;
             const int ib2 = i_block + (2 * p + 1) * T + tid;
-            if (ORDER == 3) {  // crossed accumulators: .y belongs to target a, .x to target b
-                if (ia < a.i_cnt) out[ia] = make_float4(ax[p].y, ay[p].y, az[p].y, 0.f);
-                if (ib2 < a.i_cnt) out[ib2] = make_float4(ax[p].x, ay[p].x, az[p].x, 0.f);
-            } else {
-                if (ia < a.i_cnt) out[ia] = make_float4(ax[p].x, ay[p].x, az[p].x, 0.f);
-                if (ib2 < a.i_cnt) out[ib2] = make_float4(ax[p].y, ay[p].y, az[p].y, 0.f);
+            if (!MASS_IN_LOOP) {  // the uniform g_fParticleMass factor, once per (target, segment) partial
+                const float2 m = make_float2(MAPC_PARTICLE_MASS, MAPC_PARTICLE_MASS);
+                ax[p] = __fmul2_rn(ax[p], m);
+                ay[p] = __fmul2_rn(ay[p], m);
+                az[p] = __fmul2_rn(az[p], m);
             }
+            if (ia < a.i_cnt) out[ia] = make_float4(ax[p].x, ay[p].x, az[p].x, 0.f);
+            if (ib2 < a.i_cnt) out[ib2] = make_float4(ax[p].y, ay[p].y, az[p].y, 0.f);
         }
 
         if (FUSE) {

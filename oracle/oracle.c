@@ -29,7 +29,13 @@ int mapo_max_threads(void)
 /* Compute.cpp:544  param[1] = int(ceil(N / float(BLOCK_SIZE))) */
 int mapo_num_tiles(int n) { return (n + MAPO_TILE - 1) / MAPO_TILE; }
 
-int mapo_default_segments(int n) { return n >= 131072 ? 8 : 32; }
+int mapo_default_segments(int n)
+{
+    if (n < 131072) return 32;
+    int s = 8;
+    while (s < 64 && (long long)s * 65536 < n) s *= 2;   /* chains of at most 65,536 terms */
+    return s;
+}
 
 void mapo_segment_range(int n_sources, int S, int s, int *j0, int *j1)
 {
@@ -81,10 +87,12 @@ void mapo_body_body_interaction_mirrored(float ai[3], const float bj[4], const f
     float inv = 1.0f / sqrtf(d2);
     float inv2 = inv * inv;
     float inv3 = inv2 * inv;
-    float s = inv3 * mass;
-    ai[0] = fmaf(dx, s, ai[0]);
-    ai[1] = fmaf(dy, s, ai[1]);
-    ai[2] = fmaf(dz, s, ai[2]);
+    /* the kernel leaves the uniform mass out of the pair and scales each segment partial once;
+     * `mass` is applied by the caller (mapo_accel_*: partial *= mass) */
+    (void)mass;
+    ai[0] = fmaf(dx, inv3, ai[0]);
+    ai[1] = fmaf(dy, inv3, ai[1]);
+    ai[2] = fmaf(dz, inv3, ai[2]);
 }
 
 void mapo_accel_allpairs_scalar(const mapo_posvelo *in, int n_sources, int S, int flavour,
@@ -102,6 +110,9 @@ void mapo_accel_allpairs_scalar(const mapo_posvelo *in, int n_sources, int S, in
                     mapo_body_body_interaction(p, in[j].pos, in[i].pos, MAPO_PARTICLE_MASS, 1);
                 else
                     mapo_body_body_interaction_mirrored(p, in[j].pos, in[i].pos, MAPO_PARTICLE_MASS);
+            }
+            if (flavour != MAPO_LITERAL) {                    /* once per (target, segment) partial */
+                p[0] *= MAPO_PARTICLE_MASS; p[1] *= MAPO_PARTICLE_MASS; p[2] *= MAPO_PARTICLE_MASS;
             }
             total[0] += p[0];
             total[1] += p[1];
@@ -163,13 +174,12 @@ static void segment_block_mirrored(const mapo_posvelo *in, int j0, int j1,
             float inv = 1.0f / sqrtf(d2);
             float inv2 = inv * inv;
             float inv3 = inv2 * inv;
-            float s = inv3 * mass;
-            ax[l] = fmaf(dx, s, ax[l]);
-            ay[l] = fmaf(dy, s, ay[l]);
-            az[l] = fmaf(dz, s, az[l]);
+            ax[l] = fmaf(dx, inv3, ax[l]);
+            ay[l] = fmaf(dy, inv3, ay[l]);
+            az[l] = fmaf(dz, inv3, az[l]);
         }
     }
-    for (int l = 0; l < LANES; ++l) { px[l] = ax[l]; py[l] = ay[l]; pz[l] = az[l]; }
+    for (int l = 0; l < LANES; ++l) { px[l] = ax[l] * mass; py[l] = ay[l] * mass; pz[l] = az[l] * mass; }
 }
 
 void mapo_accel_allpairs(const mapo_posvelo *in, int n_sources, int S, int flavour,

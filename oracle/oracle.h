@@ -44,7 +44,8 @@ enum { MAPO_LITERAL = 0, MAPO_MIRRORED = 1 };
 
 /* dimx of Compute.cpp:544 */
 int  mapo_num_tiles(int n);
-/* canonical segment count for n sources: 8 when n >= 131072, else 32 */
+/* canonical segment count for n sources: 32 below 131072; from there 8, doubling (up to 64) so that
+ * no segment exceeds 65,536 sources */
 int  mapo_default_segments(int n);
 /* j range [j0, j1) of segment s out of S over n_sources sources */
 void mapo_segment_range(int n_sources, int S, int s, int *j0, int *j1);
@@ -55,7 +56,8 @@ int  mapo_num_targets(int n, int n_active);
 void mapo_body_body_interaction(float ai[3], const float bj[4], const float bi[4],
                                 float mass, int particles);
 /* same pair with the contractions the CUDA kernel uses (explicit fmaf, softening folded
- * into the first fma of the dot product); 1.0f/sqrtf stands in for MUFU.RSQ. */
+ * into the first fma of the dot product); 1.0f/sqrtf stands in for MUFU.RSQ.  Like the kernel it
+ * leaves the uniform mass factor OUT: the caller scales each segment partial by the mass once. */
 void mapo_body_body_interaction_mirrored(float ai[3], const float bj[4], const float bi[4],
                                          float mass);
 

@@ -111,8 +111,12 @@ def body_body_interaction(ai, bj, bi, mass=70000.0, particles=1, flavour=LITERAL
         load().mapo_body_body_interaction(a.ctypes.data_as(fp), j.ctypes.data_as(fp), i.ctypes.data_as(fp),
                                           mass, particles)
     else:
-        load().mapo_body_body_interaction_mirrored(a.ctypes.data_as(fp), j.ctypes.data_as(fp),
+        # the mirrored pair leaves the uniform mass out (the kernel scales each segment partial once):
+        # evaluate the pair from zero, scale, then add -- what a one-pair segment does
+        t = np.zeros(3, dtype=np.float32)
+        load().mapo_body_body_interaction_mirrored(t.ctypes.data_as(fp), j.ctypes.data_as(fp),
                                                    i.ctypes.data_as(fp), mass)
+        a = (a + t * np.float32(mass)).astype(np.float32)
     return a
 
 

@@ -42,8 +42,11 @@ def test_constants_match_reference(mapc):
 
 
 def test_plan_segments_matches_oracle_rule(mapc, oracle):
-    for n in (1, 64, 1000, 10_000, 131_071, 131_072, 262_144, 1_048_576, 4_194_304):
+    for n in (1, 64, 1000, 10_000, 131_071, 131_072, 262_144, 524_288, 524_289, 741_376, 1_048_576, 2_097_153,
+              4_194_304, 8_000_000):
         assert mapc.plan_segments(n) == oracle.default_segments(n)
+    assert [mapc.plan_segments(n) for n in (10_000, 262_144, 524_288, 741_376, 1_048_576, 4_194_304)] == \
+        [32, 8, 8, 16, 16, 64]
 
 
 def test_no_cpu_fallback(mapc):

@@ -76,11 +76,13 @@ def test_weak_scaling_sizes_and_shards(mapc):
 
 def test_local_segment_classification(mapc):
     d = mapc.dist
-    # N = 1,048,576 on 8 ranks: S = 8, segment r is exactly rank r's shard
+    # N = 1,048,576 on 8 ranks with 8 segments: segment r is exactly rank r's shard; with the canonical
+    # 16 segments of that size every rank owns two
     n = 1_048_576
     for r in range(8):
         first, count = d.shard_range(n, r, 8)
         assert d.local_segments(n, 8, first, count) == [r]
+        assert d.local_segments(n, 16, first, count) == [2 * r, 2 * r + 1]
     # 2 ranks: 4 local segments each
     assert d.local_segments(n, 8, 0, n // 2) == [0, 1, 2, 3]
     # ragged: N = 10,000 (157 tiles, S = 32) on 2 ranks -- a segment straddling the shard edge is remote

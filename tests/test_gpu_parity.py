@@ -364,7 +364,7 @@ def test_batched_steps_equal_single_steps(mapc, gpu):
 @pytest.mark.parametrize("n", [1, 2, 63, 65, 129])
 def test_tiny_and_ragged_sizes(mapc, oracle, gpu, n):
     """Edge sizes: a single body (self-pair only: exactly zero force), sizes straddling the 64-body tile."""
-    p = mapc.ic.uniform_sphere(n, 50.0, seed=100 + n, speed=3.0)
+    p = mapc.ic.uniform_sphere(n, 500.0, seed=100 + n, speed=3.0)
     got = gpu_steps(mapc, p, 3)
     ref = p
     for _ in range(3):
@@ -423,3 +423,22 @@ def test_baseline_configs_4_and_5_subsampled_parity(mapc, oracle, gpu, name, n):
     assert max(err.values()) <= TOL_1, err
     dv = got["velo"][:, :3].astype(np.float64) - p["velo"][:, :3].astype(np.float64)   # = accel * dt
     assert np.all(np.abs(dv.sum(axis=0)) < 1e-4 * np.abs(dv).sum(axis=0))
+
+
+def test_mass_in_loop_variant_matches_literal_order(mapc, oracle, gpu):
+    """MAPC_MASS_IN_LOOP=1 selects the kernel that multiplies by g_fParticleMass per pair, exactly where
+    the shader does (nBodyGravityCS.hlsl:54); the default scales each segment partial once.  Both must
+    meet the stated tolerance against the LITERAL oracle, and they differ from each other only at
+    rounding level."""
+    n = 10_000
+    p = mapc.ic.lattice_sphere(n, 2000.0, seed=2, speed=1.0)
+    default = gpu_steps(mapc, p, 1)
+    try:
+        os.environ["MAPC_MASS_IN_LOOP"] = "1"
+        inloop = gpu_steps(mapc, p, 1)
+    finally:
+        os.environ.pop("MAPC_MASS_IN_LOOP", None)
+    lit = oracle.step_allpairs(p, flavour=oracle.LITERAL)
+    assert_close(oracle, default, lit, TOL_1, "default (mass per partial) vs literal")
+    assert_close(oracle, inloop, lit, TOL_1, "mass in loop vs literal")
+    assert_close(oracle, inloop, default, 2e-6, "mass in loop vs default")

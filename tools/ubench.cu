@@ -161,7 +161,7 @@ static double g_peak_tflops = 74.45;
 static int g_segments = 8;  // canonical S (argv[3])
 static int g_targets = 0;   // 0 = all bodies are targets; otherwise a shard of that many (multi-GPU shapes)
 
-template <int P, int T, int TJ, int U, int MINB, int ORDER = 0, bool TMA = false>
+template <int P, int T, int TJ, int U, int MINB, int ORDER = 0, bool TMA = false, bool INLOOP = false>
 void run_force(const float4 *pos, float4 *partial, int n, Timer &t)
 {
     const int n_tgt = g_targets > 0 ? g_targets : n;
@@ -178,7 +178,7 @@ void run_force(const float4 *pos, float4 *partial, int n, Timer &t)
     for (int s = 0; s < S; ++s) args.segs.ids[s] = s;
     const int per_block = T * 2 * P;
     args.n_iblocks = (n_tgt + per_block - 1) / per_block;
-    auto kernel = mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, false, false, TMA>;
+    auto kernel = mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, false, false, TMA, INLOOP>;
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, T, 0));
     cudaFuncAttributes fa;
@@ -187,8 +187,8 @@ void run_force(const float4 *pos, float4 *partial, int n, Timer &t)
     const dim3 grid(args.n_iblocks, S);
     const float ms = t.best([&] { kernel<<<grid, T>>>(args); }, 4);
     const double ginter = (double)n * n_tgt / (ms * 1e-3) / 1e9;
-    printf("force %s %s P=%d T=%3d TJ=%3d U=%d minB=%2d regs=%3d occ=%2d blk/SM (%2d warps) cells=%5lld : %8.3f ms %8.1f G int/s %5.1f %% of %.2f TF\n",
-           TMA ? "tma-stage" : "ldg-stage", ORDER == 0 ? "pair-major" : (ORDER == 2 ? "op-major  " : (ORDER == 4 ? "mass-hoist" : "crossed-sc")), P, T, TJ, U, MINB, fa.numRegs, occ, occ * T / 32, cells, ms, ginter,
+    printf("force %s %s %s P=%d T=%3d TJ=%3d U=%d minB=%2d regs=%3d occ=%2d blk/SM (%2d warps) cells=%5lld : %8.3f ms %8.1f G int/s %5.1f %% of %.2f TF\n",
+           TMA ? "tma-stage" : "ldg-stage", INLOOP ? "mass-in-loop    " : "mass-per-partial", ORDER == 0 ? "pair-major" : "op-major  ", P, T, TJ, U, MINB, fa.numRegs, occ, occ * T / 32, cells, ms, ginter,
            100.0 * ginter * 20.0 / 1e3 / g_peak_tflops, g_peak_tflops);
 }
 
@@ -432,9 +432,9 @@ int main(int argc, char **argv)
     run_force<2, 64, 64, 8, 8, 0>(pos, partial, n, t);
     run_force<1, 64, 64, 8, 16, 0>(pos, partial, n, t);
     run_force<1, 32, 64, 8, 32, 0>(pos, partial, n, t);
-    run_force<4, 256, 256, 8, 2, 4>(pos, partial, n, t);   // experiment: x mass hoisted (11 lane-ops)
-    run_force<4, 128, 256, 8, 4, 4>(pos, partial, n, t);
-    run_force<2, 128, 256, 4, 4, 4>(pos, partial, n, t);
+    run_force<4, 256, 256, 8, 2, 0, false, true>(pos, partial, n, t);   // the shader's per-pair mass multiply (12 lane-ops)
+    run_force<4, 128, 256, 8, 4, 0, false, true>(pos, partial, n, t);
+    run_force<2, 128, 256, 4, 4, 2, false, true>(pos, partial, n, t);
     run_force<4, 256, 256, 8, 2, 0, true>(pos, partial, n, t);
     run_force<4, 128, 256, 8, 4, 0, true>(pos, partial, n, t);
     run_force<2, 128, 256, 4, 4, 2, true>(pos, partial, n, t);
@@ -452,9 +452,9 @@ int main(int argc, char **argv)
         CK(cudaMemset(partial, 0, sizeof(float4) * n * 8));
         CK(cudaMemset(partial2, 0, sizeof(float4) * n * 8));
         args.partial = partial;
-        mapc::force_cells_kernel<4, 256, 256, 8, 2, 0, false, false, false><<<dim3(args.n_iblocks, 8), 256>>>(args);
+        mapc::force_cells_kernel<4, 256, 256, 8, 2, 0, false, false, false, false><<<dim3(args.n_iblocks, 8), 256>>>(args);
         args.partial = partial2;
-        mapc::force_cells_kernel<4, 256, 256, 8, 2, 0, false, false, true><<<dim3(args.n_iblocks, 8), 256>>>(args);
+        mapc::force_cells_kernel<4, 256, 256, 8, 2, 0, false, false, true, false><<<dim3(args.n_iblocks, 8), 256>>>(args);
         CK(cudaDeviceSynchronize());
         std::vector<float4> a((size_t)n * 8), b((size_t)n * 8);
         CK(cudaMemcpy(a.data(), partial, sizeof(float4) * a.size(), cudaMemcpyDeviceToHost));
