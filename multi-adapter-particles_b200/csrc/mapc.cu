@@ -433,7 +433,7 @@ void resolve_timers(mapc_compute *c, bool block)
 }
 
 // grid = (target blocks, segments of this launch): one cell per thread block
-template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER, bool INLOOP>
+template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER, bool INLOOP, bool TMA>
 mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream_t stream)
 {
     dim3 grid((unsigned)args.n_iblocks, (unsigned)args.segs.count, 1);
@@ -450,25 +450,37 @@ mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        MAPC_CUDA(cudaLaunchKernelEx(&cfg, mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER, false, INLOOP>, args));
+        MAPC_CUDA(cudaLaunchKernelEx(&cfg, mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER, TMA, INLOOP>, args));
     } else {
-        mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER, false, INLOOP><<<grid, T, 0, stream>>>(args);
+        mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER, TMA, INLOOP><<<grid, T, 0, stream>>>(args);
     }
     MAPC_CUDA(cudaGetLastError());
     ++c->launches;
     return MAPC_OK;
 }
 
+// Source staging: LDG/STS with register prefetch by default.  MAPC_TMA=1 switches the 256-body-stage
+// shapes to 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP): bit-identical, and measured a
+// wash -- +0.7 % for the unfused kernel in tools/ubench, -0.8 % for the fused kernel the library runs
+// (24.29 vs 24.09 ms at N = 262,144) -- so it stays off.
 template <bool FUSE, bool PEER = false, bool INLOOP = false>
 mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::StepArgs &args, cudaStream_t stream)
 {
     if (args.segs.count == 0 || args.i_cnt <= 0) return MAPC_OK;
-    if (pl.pairs == 4 && pl.threads == 256) return launch_force<4, 256, 256, 8, 2, 0, FUSE, PEER, INLOOP>(c, args, stream);
-    if (pl.pairs == 4 && pl.threads == 128) return launch_force<4, 128, 256, 8, 4, 0, FUSE, PEER, INLOOP>(c, args, stream);
-    if (pl.pairs == 2 && pl.threads == 128) return launch_force<2, 128, 256, 4, 4, 2, FUSE, PEER, INLOOP>(c, args, stream);
-    if (pl.pairs == 2 && pl.threads == 64) return launch_force<2, 64, 64, 4, 8, 2, FUSE, PEER, INLOOP>(c, args, stream);
-    if (pl.pairs == 1 && pl.threads == 64) return launch_force<1, 64, 64, 8, 16, 0, FUSE, PEER, INLOOP>(c, args, stream);
-    return launch_force<1, 32, 64, 8, 32, 0, FUSE, PEER, INLOOP>(c, args, stream);
+    constexpr bool kTma = FUSE && !PEER && !INLOOP;
+    const bool tma = kTma && env_int("MAPC_TMA", 0) != 0;
+    if (pl.pairs == 4 && pl.threads == 256)
+        return tma ? launch_force<4, 256, 256, 8, 2, 0, FUSE, PEER, INLOOP, kTma>(c, args, stream)
+                   : launch_force<4, 256, 256, 8, 2, 0, FUSE, PEER, INLOOP, false>(c, args, stream);
+    if (pl.pairs == 4 && pl.threads == 128)
+        return tma ? launch_force<4, 128, 256, 8, 4, 0, FUSE, PEER, INLOOP, kTma>(c, args, stream)
+                   : launch_force<4, 128, 256, 8, 4, 0, FUSE, PEER, INLOOP, false>(c, args, stream);
+    if (pl.pairs == 2 && pl.threads == 128)
+        return tma ? launch_force<2, 128, 256, 4, 4, 2, FUSE, PEER, INLOOP, kTma>(c, args, stream)
+                   : launch_force<2, 128, 256, 4, 4, 2, FUSE, PEER, INLOOP, false>(c, args, stream);
+    if (pl.pairs == 2 && pl.threads == 64) return launch_force<2, 64, 64, 4, 8, 2, FUSE, PEER, INLOOP, false>(c, args, stream);
+    if (pl.pairs == 1 && pl.threads == 64) return launch_force<1, 64, 64, 8, 16, 0, FUSE, PEER, INLOOP, false>(c, args, stream);
+    return launch_force<1, 32, 64, 8, 32, 0, FUSE, PEER, INLOOP, false>(c, args, stream);
 }
 
 // targets of this shard that a Simulate(n_active) updates, as a count from i_first

@@ -225,6 +225,11 @@ def test_launch_geometry_does_not_change_bits(mapc, gpu):
         os.environ["MAPC_FUSE"] = "0"
         assert gpu_steps(mapc, p, 2).tobytes() == base.tobytes(), "unfused path differs"
         os.environ.pop("MAPC_FUSE")
+        os.environ["MAPC_TMA"] = "1"            # TMA bulk-copy staging instead of LDG/STS
+        for pairs, threads in ((4, 256), (4, 128), (2, 128)):
+            os.environ["MAPC_PLAN_PAIRS"], os.environ["MAPC_PLAN_THREADS"] = str(pairs), str(threads)
+            assert gpu_steps(mapc, p, 2).tobytes() == base.tobytes(), ("TMA", pairs, threads)
+        os.environ.pop("MAPC_TMA")
         for pairs, threads in ((4, 256), (4, 128), (2, 128), (2, 64), (1, 64), (1, 32)):
             os.environ["MAPC_PLAN_PAIRS"], os.environ["MAPC_PLAN_THREADS"] = str(pairs), str(threads)
             with mapc.Compute(n, 0) as c:
@@ -233,6 +238,7 @@ def test_launch_geometry_does_not_change_bits(mapc, gpu):
             assert gpu_steps(mapc, p, 2).tobytes() == base.tobytes(), (pairs, threads)
     finally:
         os.environ.pop("MAPC_FUSE", None)
+        os.environ.pop("MAPC_TMA", None)
         os.environ.pop("MAPC_PLAN_PAIRS", None)
         os.environ.pop("MAPC_PLAN_THREADS", None)
 
