@@ -303,8 +303,8 @@ int env_int(const char *name, int dflt)
 // target lanes the last block leaves idle.  The shape changes neither the arithmetic nor its order
 // (only S does), so it is free to vary with N, the shard size and the device.
 struct Shape { int pairs, threads; float efficiency; };
-constexpr Shape kShapes[6] = {{4, 256, 0.719f}, {4, 128, 0.714f}, {2, 128, 0.717f},
-                              {2, 64, 0.700f},  {1, 64, 0.680f},  {1, 32, 0.668f}};
+constexpr Shape kShapes[6] = {{4, 256, 0.763f}, {4, 128, 0.753f}, {2, 128, 0.734f},
+                              {2, 64, 0.734f},  {1, 64, 0.728f},  {1, 32, 0.722f}};
 
 Plan make_plan(int n_targets, int n_sources, int sm_count)
 {
