@@ -46,12 +46,18 @@ struct mapc_fence {
     std::vector<mapc::GatedStream *> waiters;     // streams gated on a value of this fence
     std::vector<cudaEvent_t> spare;               // completed signals' events, reused instead of re-created
     std::vector<int> spare_device;
+    // "light" signals: the signalling kernel itself writes `word` when it finishes, and nothing is put on
+    // the stream for the signal.  A later wait on another stream records an event on `light_stream` then
+    // (everything submitted to it so far, hence the signalling kernel, is covered).
+    cudaStream_t light_stream = nullptr;
+    int light_device = -1;
+    uint64_t light_value = 0;                     // highest value signalled this way
 };
 
 namespace mapc {
 
 struct StreamOp {
-    enum Kind { kWait, kSignal, kCall } kind;
+    enum Kind { kWait, kSignal, kSignalLight, kCall } kind;
     mapc_fence *fence;
     uint64_t value;
     std::function<mapc_status()> fn;
@@ -75,6 +81,7 @@ inline bool fence_ready(const mapc_fence *f, uint64_t value)
 mapc_status gs_drain(GatedStream *gs);
 mapc_status gs_wait(GatedStream *gs, mapc_fence *f, uint64_t value);
 mapc_status gs_signal(GatedStream *gs, mapc_fence *f, uint64_t value);
+mapc_status gs_signal_light(GatedStream *gs, mapc_fence *f, uint64_t value);   // see mapc_fence::light_stream
 mapc_status gs_call(GatedStream *gs, std::function<mapc_status()> fn);
 void gs_detach(GatedStream *gs);                 // before a gated stream goes away
 void fence_notify(mapc_fence *f);                // a signal was submitted: replay what it unblocks

@@ -151,6 +151,20 @@ void fence_notify(mapc_fence *f)
     for (GatedStream *gs : waiters) gs_drain(gs);
 }
 
+static mapc_status fence_take_event(mapc_fence *f, int device, cudaEvent_t *out)
+{
+    for (size_t k = 0; k < f->spare.size(); ++k)
+        if (f->spare_device[k] == device) {
+            *out = f->spare[k];
+            f->spare.erase(f->spare.begin() + (long)k);
+            f->spare_device.erase(f->spare_device.begin() + (long)k);
+            return MAPC_OK;
+        }
+    DeviceGuard g(device);
+    MAPC_CUDA(cudaEventCreateWithFlags(out, cudaEventDisableTiming));
+    return MAPC_OK;
+}
+
 mapc_status fence_submit_signal(mapc_fence *f, cudaStream_t stream, int device, uint64_t value)
 {
     MAPC_TRY(load_stream_memops());
@@ -163,14 +177,7 @@ mapc_status fence_submit_signal(mapc_fence *f, cudaStream_t stream, int device, 
         f->signals.pop_front();
     }
     cudaEvent_t ev = nullptr;
-    for (size_t k = 0; k < f->spare.size(); ++k)
-        if (f->spare_device[k] == device) {
-            ev = f->spare[k];
-            f->spare.erase(f->spare.begin() + (long)k);
-            f->spare_device.erase(f->spare_device.begin() + (long)k);
-            break;
-        }
-    if (!ev) MAPC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    MAPC_TRY(fence_take_event(f, device, &ev));
     MAPC_CUDA(cudaEventRecord(ev, stream));
     const CUresult r = g_write64((CUstream)stream, (CUdeviceptr)(uintptr_t)f->word, value,
                                  CU_STREAM_WRITE_VALUE_DEFAULT);
@@ -192,6 +199,19 @@ mapc_status fence_submit_wait(mapc_fence *f, cudaStream_t stream, uint64_t value
             MAPC_CUDA(cudaStreamWaitEvent(stream, sig.event, 0));
             return MAPC_OK;
         }
+    if (f->light_stream != nullptr && f->light_value >= value) {
+        // signalled by a kernel that writes the word itself: make the dependency CUDA-visible now, with an
+        // event that covers everything submitted to the signalling stream so far
+        cudaEvent_t ev = nullptr;
+        MAPC_TRY(fence_take_event(f, f->light_device, &ev));
+        {
+            DeviceGuard g(f->light_device);
+            MAPC_CUDA(cudaEventRecord(ev, f->light_stream));
+        }
+        f->signals.push_back(FenceSignal{f->light_value, ev, f->light_device});
+        MAPC_CUDA(cudaStreamWaitEvent(stream, ev, 0));
+        return MAPC_OK;
+    }
     // submitted >= value but no event: the value was signalled from the host and is visible already
     return MAPC_OK;
 }
@@ -202,6 +222,22 @@ static mapc_status run_op(GatedStream *gs, StreamOp &op)
     switch (op.kind) {
     case StreamOp::kWait: return fence_submit_wait(op.fence, gs->stream, op.value);
     case StreamOp::kSignal: return fence_submit_signal(op.fence, gs->stream, gs->device, op.value);
+    case StreamOp::kSignalLight: {
+        // the kernel just enqueued on this stream writes the word when it finishes; no stream operation
+        mapc_fence *f = op.fence;
+        const uint64_t done = fence_completed(f);
+        while (f->signals.size() > 4 && f->signals.front().value <= done) {
+            f->spare.push_back(f->signals.front().event);
+            f->spare_device.push_back(f->signals.front().device);
+            f->signals.pop_front();
+        }
+        f->light_stream = gs->stream;
+        f->light_device = gs->device;
+        if (op.value > f->light_value) f->light_value = op.value;
+        if (op.value > f->submitted) f->submitted = op.value;
+        fence_notify(f);
+        return MAPC_OK;
+    }
     default: return op.fn();
     }
 }
@@ -249,6 +285,11 @@ mapc_status gs_wait(GatedStream *gs, mapc_fence *f, uint64_t value)
 mapc_status gs_signal(GatedStream *gs, mapc_fence *f, uint64_t value)
 {
     return gs_push(gs, StreamOp{StreamOp::kSignal, f, value, nullptr});
+}
+
+mapc_status gs_signal_light(GatedStream *gs, mapc_fence *f, uint64_t value)
+{
+    return gs_push(gs, StreamOp{StreamOp::kSignalLight, f, value, nullptr});
 }
 
 mapc_status gs_call(GatedStream *gs, std::function<mapc_status()> fn)
@@ -385,6 +426,7 @@ struct mapc_compute {
     unsigned long long *stamps = nullptr;      // pinned host: [slot][begin, end] in ns
     unsigned *done = nullptr;                  // device: target blocks integrated this step
     unsigned long long *stamp_begin_next = nullptr, *stamp_end_next = nullptr;  // for the next force launch(es)
+    unsigned long long fence_write_next = 0;   // != 0: the step's last block writes this value to the fence word
     uint64_t t_next = 0, t_resolved = 0;
     float ms_average = 0.f, ms_last = 0.f;
     std::vector<float> step_log;  // raw samples not yet handed out by mapc_compute_step_times
@@ -852,7 +894,8 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
 
 // `steps` consecutive steps (ping-pong starting with write side b0) inside ONE timer pair.
 static mapc_status enqueue_steps(mapc_compute *c, uint32_t b0, int n_targets, int n_sources, float delta_time,
-                                 float damping, mapc_force_mode mode, int steps, uint64_t fence_value_after)
+                                 float damping, mapc_force_mode mode, int steps, uint64_t fence_value_after,
+                                 bool kernel_signals)
 {
     const bool timers = env_int("MAPC_TIMERS", 1) != 0;   // experiment switch
     resolve_timers(c, false);
@@ -875,9 +918,11 @@ static mapc_status enqueue_steps(mapc_compute *c, uint32_t b0, int n_targets, in
         c->pdl_next = pdl && k > 0;
         c->stamp_begin_next = (stamped && k == 0) ? &c->stamps[2 * slot] : nullptr;
         c->stamp_end_next = (stamped && k == steps - 1) ? &c->stamps[2 * slot + 1] : nullptr;
+        c->fence_write_next = (kernel_signals && k == steps - 1) ? fence_value_after : 0;
         const mapc_status st = enqueue_one(c, (b0 + (uint32_t)k) & 1u, n_targets, n_sources, delta_time, damping, mode);
         c->pdl_next = false;
         c->stamp_begin_next = c->stamp_end_next = nullptr;
+        c->fence_write_next = 0;
         if (st != MAPC_OK) return st;
     }
     if (!timers) return MAPC_OK;
@@ -931,6 +976,8 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             args.done = c->done;
             args.stamp_begin = c->stamp_begin_next;   // consumed by the first launch of the step
             args.stamp_end = c->stamp_end_next;       // every launch: whichever finishes the step writes it
+            args.fence_word = c->fence_write_next ? (unsigned long long *)c->fence->word : nullptr;
+            args.fence_value = c->fence_write_next;
             mapc::SegList local{0, {}}, remote{0, {}};
             int owner[MAPC_MAX_SEGMENTS];
             bool peer = c->peer_mode && fuse && n_sources == (int)c->n && env_int("MAPC_PEER", 1) != 0 &&
@@ -1042,13 +1089,21 @@ mapc_status mapc_compute_simulate_steps(mapc_compute *c, int num_active_particle
     const int n_sources = num_active_particles;
     const mapc_force_mode mode = c->mode;
     const uint64_t fence_value_after = c->fence_value + (uint64_t)(steps - 1);
+    // Unsharded fused all-pairs steps signal the fence from inside the kernel (the block that finishes the
+    // step writes the word): nothing but the kernel goes on the stream.  Everything else uses the
+    // event + memory-operation signal.
+    const bool kernel_signals = c->world == 1 && mode == MAPC_FORCE_ALLPAIRS && n_targets > 0 &&
+                                env_int("MAPC_FUSE", 1) != 0 && env_int("MAPC_TIMERS", 1) != 0 &&
+                                env_int("MAPC_TIMER_EVENTS", 0) == 0 && env_int("MAPC_KERNEL_FENCE", 1) != 0;
     MAPC_TRY(mapc::gs_call(&c->gcompute, [=]() -> mapc_status {
-        return enqueue_steps(c, b, n_targets, n_sources, delta_time, damping, mode, steps, fence_value_after);
+        return enqueue_steps(c, b, n_targets, n_sources, delta_time, damping, mode, steps, fence_value_after,
+                             kernel_signals);
     }));
 
     // MoveToNextFrame, Compute.cpp:993-1004 (a batch consumes one fence value per step and signals the last)
     c->fence_value += (uint64_t)(steps - 1);
-    MAPC_TRY(mapc::gs_signal(&c->gcompute, c->fence, c->fence_value));
+    if (kernel_signals) MAPC_TRY(mapc::gs_signal_light(&c->gcompute, c->fence, c->fence_value));
+    else MAPC_TRY(mapc::gs_signal(&c->gcompute, c->fence, c->fence_value));
     c->fence_value++;
     if (steps & 1) c->buffer_index = 1u - c->buffer_index;
     return MAPC_OK;

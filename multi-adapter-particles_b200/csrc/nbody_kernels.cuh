@@ -180,6 +180,10 @@ struct StepArgs {
     unsigned long long *stamp_begin;   // pinned host memory, or null
     unsigned long long *stamp_end;     // pinned host memory, or null
     unsigned *done;                    // target blocks integrated so far this step (device)
+    // fence signal from inside the kernel (ID3D12CommandQueue::Signal after the Dispatch, Compute.cpp:999):
+    // the same last block stores fence_value to the fence word (pinned host memory) -- or null
+    unsigned long long *fence_word;
+    unsigned long long fence_value;
 };
 
 __device__ __forceinline__ unsigned long long global_timer_ns()
@@ -422,6 +426,10 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                         __threadfence();
                         *a.stamp_end = global_timer_ns();
                         __threadfence_system();
+                        if (a.fence_word != nullptr) {
+                            *reinterpret_cast<volatile unsigned long long *>(a.fence_word) = a.fence_value;
+                            __threadfence_system();
+                        }
                     }
                 }
             }
