@@ -912,10 +912,14 @@ static mapc_status enqueue_steps(mapc_compute *c, uint32_t b0, int n_targets, in
     } else if (timers) {
         MAPC_CUDA(cudaEventRecord(c->t_begin[slot], c->compute));  // BeginTimer, Compute.cpp:1020
     }
-    const bool pdl = steps > 1 && c->world == 1 && mode == MAPC_FORCE_ALLPAIRS && env_int("MAPC_FUSE", 1) != 0 &&
+    // Programmatic dependent launch for every unsharded fused step, not only inside a batch: since such a
+    // Simulate puts nothing but its kernel on the stream (timer stamps and fence signal are written by the
+    // kernel), back-to-back Simulate calls chain kernel to kernel as well.  After any other kind of stream
+    // operation the attribute is harmless (ordinary stream order applies).
+    const bool pdl = c->world == 1 && mode == MAPC_FORCE_ALLPAIRS && env_int("MAPC_FUSE", 1) != 0 &&
                      env_int("MAPC_PDL", 1) != 0;
     for (int k = 0; k < steps; ++k) {
-        c->pdl_next = pdl && k > 0;
+        c->pdl_next = pdl;
         c->stamp_begin_next = (stamped && k == 0) ? &c->stamps[2 * slot] : nullptr;
         c->stamp_end_next = (stamped && k == steps - 1) ? &c->stamps[2 * slot + 1] : nullptr;
         c->fence_write_next = (kernel_signals && k == steps - 1) ? fence_value_after : 0;
