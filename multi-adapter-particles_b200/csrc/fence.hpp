@@ -23,6 +23,7 @@
 #include <cstdint>
 #include <deque>
 #include <functional>
+#include <string>
 #include <vector>
 
 #include "../../include/mapc.h"
@@ -68,6 +69,11 @@ struct GatedStream {
     int device = 0;
     std::deque<StreamOp> pending;
     bool draining = false;
+    // An operation that was queued behind a gate runs later, inside whichever call submits the signal
+    // it waited for -- a call that may belong to another object.  Its failure is kept here and reported
+    // by the next operation on THIS stream instead of being lost.
+    mapc_status deferred_error = MAPC_OK;
+    std::string deferred_message;
 };
 
 // implemented in mapc.cu (they need its error plumbing and driver entry points)

@@ -3,8 +3,8 @@
 // Replaces Particles/Compute.{h,cpp} of the reference for the simulation path: the D3D12 compute
 // queue, command lists, root signature / PSO, descriptor heap and cross-adapter heap become CUDA
 // streams and device buffers; ID3D12Fence becomes mapc_fence (a 64-bit word every device and the
-// host can signal / wait on); the D3D12GpuTimer becomes cudaEvent pairs with the same 20-sample
-// moving average.  There is deliberately NO CPU fallback: without a CUDA device every entry
+// host can signal / wait on); the D3D12GpuTimer becomes %globaltimer stamps written by the force
+// kernel (cudaEvent pairs for the other kernels) with the same 20-sample moving average.  There is deliberately NO CPU fallback: without a CUDA device every entry
 // point that needs one returns MAPC_ERR_NO_DEVICE / MAPC_ERR_CUDA.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -259,7 +259,13 @@ mapc_status gs_drain(GatedStream *gs)
             if (!still) w.erase(std::remove(w.begin(), w.end(), gs), w.end());
         }
         st = run_op(gs, local);
-        if (st != MAPC_OK) break;
+        if (st != MAPC_OK) {
+            if (gs->deferred_error == MAPC_OK) {   // sticky: see GatedStream::deferred_error
+                gs->deferred_error = st;
+                gs->deferred_message = g_last_error;
+            }
+            break;
+        }
     }
     gs->draining = false;
     return st;
@@ -267,6 +273,9 @@ mapc_status gs_drain(GatedStream *gs)
 
 static mapc_status gs_push(GatedStream *gs, StreamOp op)
 {
+    if (gs->deferred_error != MAPC_OK)
+        return fail(gs->deferred_error, "an earlier queued operation of this stream failed: %s",
+                    gs->deferred_message.c_str());
     if (gs->pending.empty() && !(op.kind == StreamOp::kWait && !fence_ready(op.fence, op.value)))
         return run_op(gs, op);
     if (op.kind == StreamOp::kWait) {
@@ -300,11 +309,26 @@ mapc_status gs_call(GatedStream *gs, std::function<mapc_status()> fn)
 void gs_detach(GatedStream *gs)
 {
     for (StreamOp &op : gs->pending)
-        if (op.kind == StreamOp::kWait) {
+        if (op.kind == StreamOp::kWait && op.fence) {
             auto &w = op.fence->waiters;
             w.erase(std::remove(w.begin(), w.end(), gs), w.end());
         }
     gs->pending.clear();
+}
+
+// A fence is going away: whatever is still queued against it, on any stream, becomes a no-op (its waits
+// count as satisfied, its signals have nobody left to see them).
+static void fence_scrub(mapc_fence *f)
+{
+    const std::vector<GatedStream *> waiters = f->waiters;
+    for (GatedStream *gs : waiters)
+        for (StreamOp &op : gs->pending)
+            if (op.fence == f) {
+                op.kind = StreamOp::kCall;
+                op.fence = nullptr;
+                op.fn = []() -> mapc_status { return MAPC_OK; };
+            }
+    f->waiters.clear();
 }
 
 // a stream that still has host-queued work is waiting for a signal nobody has submitted
@@ -338,6 +362,39 @@ int env_int(const char *name, int dflt)
     return (v && *v) ? atoi(v) : dflt;
 }
 
+// Every A/B switch of the library, read from the environment once per API call (so a queued, gated
+// step runs with the switches of the call that issued it).  Defaults are the measured-best path; the
+// others exist so tests and profiles can show the alternatives are the same arithmetic.
+struct Switches {
+    bool fuse;          // MAPC_FUSE=0: separate integrate_kernel instead of the last-arrival combine
+    bool pdl;           // MAPC_PDL=0: no programmatic dependent launch between consecutive steps
+    bool tma;           // MAPC_TMA=1: cp.async.bulk source staging instead of LDG/STS
+    bool shfl;          // MAPC_SHFL=1: warp-shuffle broadcast of staged sources instead of LDS broadcast
+    bool mass_in_loop;  // MAPC_MASS_IN_LOOP=1: 12-op pair with the shader's per-pair mass multiply
+    bool timers;        // MAPC_TIMERS=0: no "simulate ms" timer at all
+    bool timer_events;  // MAPC_TIMER_EVENTS=1: cudaEvent pairs instead of in-kernel stamps
+    bool kernel_fence;  // MAPC_KERNEL_FENCE=0: fence signalled by a stream operation, not by the kernel
+    bool peer;          // MAPC_PEER=0: attached peer exchange not used
+    int plan_pairs, plan_threads;  // MAPC_PLAN_PAIRS / MAPC_PLAN_THREADS: force a launch shape (0 = choose)
+};
+
+Switches read_switches()
+{
+    Switches w;
+    w.fuse = env_int("MAPC_FUSE", 1) != 0;
+    w.pdl = env_int("MAPC_PDL", 1) != 0;
+    w.tma = env_int("MAPC_TMA", 0) != 0;
+    w.shfl = env_int("MAPC_SHFL", 0) != 0;
+    w.mass_in_loop = env_int("MAPC_MASS_IN_LOOP", 0) != 0;
+    w.timers = env_int("MAPC_TIMERS", 1) != 0;
+    w.timer_events = env_int("MAPC_TIMER_EVENTS", 0) != 0;
+    w.kernel_fence = env_int("MAPC_KERNEL_FENCE", 1) != 0;
+    w.peer = env_int("MAPC_PEER", 1) != 0;
+    w.plan_pairs = env_int("MAPC_PLAN_PAIRS", 0);
+    w.plan_threads = env_int("MAPC_PLAN_THREADS", 0);
+    return w;
+}
+
 // Launch shapes (P, T) with the FMA-pipe efficiency each reaches at large N (tools/ubench,
 // profiles/): all sit on the same 67-72 % plateau, so at large N the choice barely matters, while
 // at small N what decides is how evenly the cells fall on the 4 x SMs warp schedulers and how many
@@ -347,12 +404,12 @@ struct Shape { int pairs, threads; float efficiency; };
 constexpr Shape kShapes[6] = {{4, 256, 0.763f}, {4, 128, 0.753f}, {2, 128, 0.734f},
                               {2, 64, 0.734f},  {1, 64, 0.728f},  {1, 32, 0.722f}};
 
-Plan make_plan(int n_targets, int n_sources, int sm_count)
+Plan make_plan(int n_targets, int n_sources, int sm_count, const Switches &sw)
 {
     const int S = mapc_plan_segments((uint32_t)n_sources);
     Plan best{1, 32, 0, S};
     float best_score = -1.f;
-    const int fp = env_int("MAPC_PLAN_PAIRS", 0), ft = env_int("MAPC_PLAN_THREADS", 0);
+    const int fp = sw.plan_pairs, ft = sw.plan_threads;
     for (const Shape &sh : kShapes) {
         if ((fp && fp != sh.pairs) || (ft && ft != sh.threads)) continue;
         const int per_block = sh.threads * 2 * sh.pairs;
@@ -399,6 +456,7 @@ struct mapc_compute {
 
     mapc_fence *fence = nullptr;            // m_fence
     mapc_fence *consumer_fence = nullptr;   // m_sharedRenderFence (borrowed)
+    struct mapc_consumer *consumer = nullptr;  // headless consumer attached to this producer, if any
     uint64_t fence_value = 0;               // m_fenceValue
     uint32_t buffer_index = 0;              // m_bufferIndex
 
@@ -475,9 +533,11 @@ void resolve_timers(mapc_compute *c, bool block)
 }
 
 // grid = (target blocks, segments of this launch): one cell per thread block
-template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER, bool INLOOP, bool TMA>
+template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER, bool INLOOP, bool TMA,
+          bool SHFL = false>
 mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream_t stream)
 {
+    auto kernel = mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER, TMA, INLOOP, SHFL>;
     dim3 grid((unsigned)args.n_iblocks, (unsigned)args.segs.count, 1);
     if (c->pdl_next) {
         // batched steps: the grid may be scheduled while the previous step's grid drains (the kernel
@@ -492,37 +552,45 @@ mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        MAPC_CUDA(cudaLaunchKernelEx(&cfg, mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER, TMA, INLOOP>, args));
+        MAPC_CUDA(cudaLaunchKernelEx(&cfg, kernel, args));
     } else {
-        mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER, TMA, INLOOP><<<grid, T, 0, stream>>>(args);
+        kernel<<<grid, T, 0, stream>>>(args);
     }
     MAPC_CUDA(cudaGetLastError());
     ++c->launches;
     return MAPC_OK;
 }
 
-// Source staging: LDG/STS with register prefetch by default.  MAPC_TMA=1 switches the 256-body-stage
-// shapes to 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP): bit-identical, and measured a
-// wash -- +0.7 % for the unfused kernel in tools/ubench, -0.8 % for the fused kernel the library runs
-// (24.29 vs 24.09 ms at N = 262,144) -- so it stays off.
+// Source staging: LDG/STS with register prefetch and a uniform-address LDS.128 broadcast per source by
+// default.  Two bit-identical alternatives exist for the A/B (fused, non-peer, 11-op kernel only):
+//   kStageTma   MAPC_TMA=1   1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) fill the stages
+//                            of the 256-body-stage shapes: a wash, +0.7 % unfused in tools/ubench, -0.8 %
+//                            for the fused kernel (24.29 vs 24.09 ms at N = 262,144);
+//   kStageShfl  MAPC_SHFL=1  warp-shuffle broadcast of the staged bodies instead of the LDS broadcast.
+enum Staging { kStageDefault = 0, kStageTma = 1, kStageShfl = 2 };
+
 template <bool FUSE, bool PEER = false, bool INLOOP = false>
-mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::StepArgs &args, cudaStream_t stream)
+mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::StepArgs &args, cudaStream_t stream,
+                               Staging staging)
 {
     if (args.segs.count == 0 || args.i_cnt <= 0) return MAPC_OK;
-    constexpr bool kTma = FUSE && !PEER && !INLOOP;
-    const bool tma = kTma && env_int("MAPC_TMA", 0) != 0;
-    if (pl.pairs == 4 && pl.threads == 256)
-        return tma ? launch_force<4, 256, 256, 8, 2, 0, FUSE, PEER, INLOOP, kTma>(c, args, stream)
-                   : launch_force<4, 256, 256, 8, 2, 0, FUSE, PEER, INLOOP, false>(c, args, stream);
-    if (pl.pairs == 4 && pl.threads == 128)
-        return tma ? launch_force<4, 128, 256, 8, 4, 0, FUSE, PEER, INLOOP, kTma>(c, args, stream)
-                   : launch_force<4, 128, 256, 8, 4, 0, FUSE, PEER, INLOOP, false>(c, args, stream);
-    if (pl.pairs == 2 && pl.threads == 128)
-        return tma ? launch_force<2, 128, 256, 4, 4, 2, FUSE, PEER, INLOOP, kTma>(c, args, stream)
-                   : launch_force<2, 128, 256, 4, 4, 2, FUSE, PEER, INLOOP, false>(c, args, stream);
-    if (pl.pairs == 2 && pl.threads == 64) return launch_force<2, 64, 64, 4, 8, 2, FUSE, PEER, INLOOP, false>(c, args, stream);
-    if (pl.pairs == 1 && pl.threads == 64) return launch_force<1, 64, 64, 8, 16, 0, FUSE, PEER, INLOOP, false>(c, args, stream);
-    return launch_force<1, 32, 64, 8, 32, 0, FUSE, PEER, INLOOP, false>(c, args, stream);
+    constexpr bool kAlt = FUSE && !PEER && !INLOOP;   // the alternatives are instantiated for this path only
+    const bool tma = kAlt && staging == kStageTma;
+    const bool shfl = kAlt && staging == kStageShfl;
+#define MAPC_SHAPE(P, T, TJ, U, MINB, ORDER, HAS_TMA)                                                          \
+    if (pl.pairs == P && pl.threads == T) {                                                                   \
+        if (HAS_TMA && tma) return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, kAlt && HAS_TMA>(c, args, stream); \
+        if (shfl) return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false, kAlt>(c, args, stream); \
+        return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false>(c, args, stream);             \
+    }
+    MAPC_SHAPE(4, 256, 256, 8, 2, 0, true)
+    MAPC_SHAPE(4, 128, 256, 8, 4, 0, true)
+    MAPC_SHAPE(2, 128, 256, 4, 4, 2, true)
+    MAPC_SHAPE(2, 64, 64, 4, 8, 2, false)
+    MAPC_SHAPE(1, 64, 64, 8, 16, 0, false)
+    MAPC_SHAPE(1, 32, 64, 8, 32, 0, false)
+#undef MAPC_SHAPE
+    return fail(MAPC_ERR_INVALID_ARGUMENT, "no kernel for launch shape P=%d T=%d", pl.pairs, pl.threads);
 }
 
 // targets of this shard that a Simulate(n_active) updates, as a count from i_first
@@ -632,6 +700,8 @@ mapc_status create_common(mapc_compute **out, uint32_t n, int device, int rank, 
 
 }  // namespace
 
+static void consumer_orphan(struct mapc_consumer *r);   // defined with the consumer, below
+
 // =================================================================================================
 extern "C" {
 
@@ -681,9 +751,11 @@ mapc_status mapc_fence_create(mapc_fence **out, uint64_t initial_value)
 mapc_status mapc_fence_destroy(mapc_fence *f)
 {
     if (!f) return MAPC_OK;
-    // nothing may stay gated on a fence that is going away: treat its waits as satisfied
+    // nothing may stay gated on a fence that is going away: treat its waits as satisfied, and strip what
+    // is queued behind OTHER gates of its references to this fence
     f->submitted = UINT64_MAX;
     mapc::fence_notify(f);
+    mapc::fence_scrub(f);
     for (mapc::FenceSignal &sig : f->signals) cudaEventDestroy(sig.event);
     for (cudaEvent_t ev : f->spare) cudaEventDestroy(ev);
     if (f->word) cudaFreeHost((void *)f->word);
@@ -783,9 +855,11 @@ mapc_status mapc_compute_destroy(mapc_compute *c)
 {
     if (!c) return MAPC_OK;
     DeviceGuard g(c->device);
+    if (c->consumer) consumer_orphan(c->consumer);   // it must not touch this producer's buffers or fence again
     // Compute::~Compute drains the queue first (Compute.cpp:104)
     mapc::gs_detach(&c->gcompute);  // host-queued work gated on a signal that never came is dropped
     if (c->compute) cudaStreamSynchronize(c->compute);
+    if (c->compute2) cudaStreamSynchronize(c->compute2);
     if (c->comm) cudaStreamSynchronize(c->comm);
     if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
     if (c->peer_mode)
@@ -812,7 +886,6 @@ mapc_status mapc_compute_destroy(mapc_compute *c)
         if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]);
         if (c->t_end[k]) cudaEventDestroy(c->t_end[k]);
     }
-    if (c->compute2) cudaStreamSynchronize(c->compute2);
     if (c->ev_step_begin) cudaEventDestroy(c->ev_step_begin);
     if (c->ev_remote_done) cudaEventDestroy(c->ev_remote_done);
     if (c->compute) cudaStreamDestroy(c->compute);
@@ -890,22 +963,21 @@ mapc_status mapc_compute_set_force_mode(mapc_compute *c, mapc_force_mode mode)
 // Enqueues one step on the compute (and comm) stream.  Runs either straight away or, when the
 // compute stream is gated on a consumer-fence value nobody has submitted yet, when that gate opens.
 static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n_sources, float delta_time,
-                               float damping, mapc_force_mode mode);
+                               float damping, mapc_force_mode mode, const Switches &sw);
 
 // `steps` consecutive steps (ping-pong starting with write side b0) inside ONE timer pair.
 static mapc_status enqueue_steps(mapc_compute *c, uint32_t b0, int n_targets, int n_sources, float delta_time,
                                  float damping, mapc_force_mode mode, int steps, uint64_t fence_value_after,
-                                 bool kernel_signals)
+                                 bool kernel_signals, const Switches &sw)
 {
-    const bool timers = env_int("MAPC_TIMERS", 1) != 0;   // experiment switch
+    const bool timers = sw.timers;
     resolve_timers(c, false);
     const int slot = (int)(c->t_next % mapc_compute::kTimerSlots);
     if (c->t_pending[slot]) resolve_timers(c, true);
     // Two timing-enabled event records cost ~8 us of stream time per step on B200 (measured at
     // N = 10,000), so the fused all-pairs kernel stamps %globaltimer itself; the event pair remains for
     // the well kernel and the unfused path.
-    const bool stamped = timers && mode == MAPC_FORCE_ALLPAIRS && n_targets > 0 && env_int("MAPC_FUSE", 1) != 0 &&
-                         env_int("MAPC_TIMER_EVENTS", 0) == 0;
+    const bool stamped = timers && mode == MAPC_FORCE_ALLPAIRS && n_targets > 0 && sw.fuse && !sw.timer_events;
     if (stamped) {
         c->stamps[2 * slot] = 0;
         c->stamps[2 * slot + 1] = 0;
@@ -916,14 +988,13 @@ static mapc_status enqueue_steps(mapc_compute *c, uint32_t b0, int n_targets, in
     // Simulate puts nothing but its kernel on the stream (timer stamps and fence signal are written by the
     // kernel), back-to-back Simulate calls chain kernel to kernel as well.  After any other kind of stream
     // operation the attribute is harmless (ordinary stream order applies).
-    const bool pdl = c->world == 1 && mode == MAPC_FORCE_ALLPAIRS && env_int("MAPC_FUSE", 1) != 0 &&
-                     env_int("MAPC_PDL", 1) != 0;
+    const bool pdl = c->world == 1 && mode == MAPC_FORCE_ALLPAIRS && sw.fuse && sw.pdl;
     for (int k = 0; k < steps; ++k) {
         c->pdl_next = pdl;
         c->stamp_begin_next = (stamped && k == 0) ? &c->stamps[2 * slot] : nullptr;
         c->stamp_end_next = (stamped && k == steps - 1) ? &c->stamps[2 * slot + 1] : nullptr;
         c->fence_write_next = (kernel_signals && k == steps - 1) ? fence_value_after : 0;
-        const mapc_status st = enqueue_one(c, (b0 + (uint32_t)k) & 1u, n_targets, n_sources, delta_time, damping, mode);
+        const mapc_status st = enqueue_one(c, (b0 + (uint32_t)k) & 1u, n_targets, n_sources, delta_time, damping, mode, sw);
         c->pdl_next = false;
         c->stamp_begin_next = c->stamp_end_next = nullptr;
         c->fence_write_next = 0;
@@ -940,7 +1011,7 @@ static mapc_status enqueue_steps(mapc_compute *c, uint32_t b0, int n_targets, in
 }
 
 static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n_sources, float delta_time,
-                               float damping, mapc_force_mode mode)
+                               float damping, mapc_force_mode mode, const Switches &sw)
 {
     const uint32_t r = 1u - b;  // read side (reads 1-b, writes b)
     bool use_peer = false;
@@ -952,9 +1023,9 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             MAPC_CUDA(cudaGetLastError());
             ++c->launches;
         } else {
-            const Plan pl = make_plan(n_targets, n_sources, c->sm_count);
+            const Plan pl = make_plan(n_targets, n_sources, c->sm_count, sw);
             MAPC_TRY(ensure_partial(c, pl.segments));
-            const bool fuse = env_int("MAPC_FUSE", 1) != 0;
+            const bool fuse = sw.fuse;
             const int key = pl.pairs * 1024 + pl.threads;
             if (fuse && c->counters_key != key) {  // arrival counters are per target block of this shape
                 MAPC_CUDA(cudaMemsetAsync(c->counters, 0, ((size_t)c->n_local / 64 + 2) * sizeof(unsigned), c->compute));
@@ -984,8 +1055,7 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             args.fence_value = c->fence_write_next;
             mapc::SegList local{0, {}}, remote{0, {}};
             int owner[MAPC_MAX_SEGMENTS];
-            bool peer = c->peer_mode && fuse && n_sources == (int)c->n && env_int("MAPC_PEER", 1) != 0 &&
-                        env_int("MAPC_MASS_IN_LOOP", 0) == 0;
+            bool peer = c->peer_mode && fuse && n_sources == (int)c->n && sw.peer && !sw.mass_in_loop;
             for (int s = 0; s < pl.segments; ++s) {
                 int j0, j1;
                 mapc::segment_range(n_sources, pl.segments, s, j0, j1);
@@ -1008,10 +1078,12 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             if (remote.count > 0) MAPC_CUDA(cudaEventRecord(c->ev_step_begin, c->compute));
             // MAPC_MASS_IN_LOOP=1: the shader's per-pair `mass * invDistCube` (12 lane-ops) instead of the
             // default once-per-partial scale (11): A/B switch, fused non-peer path only
-            const bool inloop = fuse && env_int("MAPC_MASS_IN_LOOP", 0) != 0;
+            const bool inloop = fuse && sw.mass_in_loop;
+            const Staging staging = sw.shfl ? kStageShfl : (sw.tma ? kStageTma : kStageDefault);
             auto launch = [&](cudaStream_t st) -> mapc_status {
-                if (inloop) return launch_force_shape<true, false, true>(c, pl, args, st);
-                return fuse ? launch_force_shape<true>(c, pl, args, st) : launch_force_shape<false>(c, pl, args, st);
+                if (inloop) return launch_force_shape<true, false, true>(c, pl, args, st, staging);
+                return fuse ? launch_force_shape<true>(c, pl, args, st, staging)
+                            : launch_force_shape<false>(c, pl, args, st, staging);
             };
             args.segs = local;
             MAPC_TRY(launch(c->compute));
@@ -1027,7 +1099,7 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
                         args.seg_flag[k] = c->peer_flag[o];
                     }
                     args.flag_expect = c->step_id;   // owners must have completed step_id steps
-                    MAPC_TRY((launch_force_shape<true, true>(c, pl, args, c->compute2)));
+                    MAPC_TRY((launch_force_shape<true, true>(c, pl, args, c->compute2, kStageDefault)));
                 } else {
                     MAPC_CUDA(cudaStreamWaitEvent(c->compute2, c->ev_gathered[r], 0));
                     MAPC_TRY(launch(c->compute2));
@@ -1096,12 +1168,12 @@ mapc_status mapc_compute_simulate_steps(mapc_compute *c, int num_active_particle
     // Unsharded fused all-pairs steps signal the fence from inside the kernel (the block that finishes the
     // step writes the word): nothing but the kernel goes on the stream.  Everything else uses the
     // event + memory-operation signal.
-    const bool kernel_signals = c->world == 1 && mode == MAPC_FORCE_ALLPAIRS && n_targets > 0 &&
-                                env_int("MAPC_FUSE", 1) != 0 && env_int("MAPC_TIMERS", 1) != 0 &&
-                                env_int("MAPC_TIMER_EVENTS", 0) == 0 && env_int("MAPC_KERNEL_FENCE", 1) != 0;
+    const Switches sw = read_switches();
+    const bool kernel_signals = c->world == 1 && mode == MAPC_FORCE_ALLPAIRS && n_targets > 0 && sw.fuse &&
+                                sw.timers && !sw.timer_events && sw.kernel_fence;
     MAPC_TRY(mapc::gs_call(&c->gcompute, [=]() -> mapc_status {
         return enqueue_steps(c, b, n_targets, n_sources, delta_time, damping, mode, steps, fence_value_after,
-                             kernel_signals);
+                             kernel_signals, sw);
     }));
 
     // MoveToNextFrame, Compute.cpp:993-1004 (a batch consumes one fence value per step and signals the last)
@@ -1304,7 +1376,7 @@ mapc_status mapc_compute_plan(const mapc_compute *c, int num_active_particles, i
 {
     if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
     const int n_targets = local_targets(c, num_active_particles);
-    const Plan pl = make_plan(n_targets, num_active_particles, c->sm_count);
+    const Plan pl = make_plan(n_targets, num_active_particles, c->sm_count, read_switches());
     if (pairs_per_thread) *pairs_per_thread = pl.pairs;
     if (threads_per_block) *threads_per_block = pl.threads;
     if (num_blocks) *num_blocks = pl.blocks_x * pl.segments;
@@ -1321,26 +1393,31 @@ mapc_status mapc_fp32_peak_probe(int device, int packed, float *tflops, float *m
     int sms = 0;
     MAPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     float *sink = nullptr;
-    MAPC_CUDA(cudaMalloc(&sink, 64));
-    cudaEvent_t e0, e1;
-    MAPC_CUDA(cudaEventCreate(&e0));
-    MAPC_CUDA(cudaEventCreate(&e1));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     const int iters = 8192, blocks = sms * 8, threads = 256;
     float best = 1e30f;
-    for (int rep = 0; rep < 4; ++rep) {
-        MAPC_CUDA(cudaEventRecord(e0, 0));
-        if (packed) mapc::fp32_peak_kernel<true><<<blocks, threads>>>(sink, iters, 0.999f, 0.001f);
-        else mapc::fp32_peak_kernel<false><<<blocks, threads>>>(sink, iters, 0.999f, 0.001f);
-        MAPC_CUDA(cudaEventRecord(e1, 0));
-        MAPC_CUDA(cudaEventSynchronize(e1));
-        MAPC_CUDA(cudaGetLastError());
-        float ms = 0.f;
-        MAPC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        if (rep > 0 && ms < best) best = ms;
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(sink);
+    auto body = [&]() -> mapc_status {
+        MAPC_CUDA(cudaMalloc(&sink, 64));
+        MAPC_CUDA(cudaEventCreate(&e0));
+        MAPC_CUDA(cudaEventCreate(&e1));
+        for (int rep = 0; rep < 4; ++rep) {
+            MAPC_CUDA(cudaEventRecord(e0, 0));
+            if (packed) mapc::fp32_peak_kernel<true><<<blocks, threads>>>(sink, iters, 0.999f, 0.001f);
+            else mapc::fp32_peak_kernel<false><<<blocks, threads>>>(sink, iters, 0.999f, 0.001f);
+            MAPC_CUDA(cudaEventRecord(e1, 0));
+            MAPC_CUDA(cudaEventSynchronize(e1));
+            MAPC_CUDA(cudaGetLastError());
+            float ms = 0.f;
+            MAPC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        return MAPC_OK;
+    };
+    const mapc_status st = body();
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (sink) cudaFree(sink);
+    if (st != MAPC_OK) return st;
     // 32 lane-FMAs per thread per iteration in both variants (16 x f32x2 or 32 scalar)
     const double flops = 2.0 * 32.0 * iters * (double)blocks * threads;
     if (tflops) *tflops = (float)(flops / (best * 1e-3) / 1e12);
@@ -1376,6 +1453,23 @@ struct mapc_consumer {
     uint64_t copies = 0;
 };
 
+// The producer is being destroyed first: finish what the consumer still has in flight against the
+// producer's buffers, then cut every reference to it.  Draw fails loudly from now on.
+static void consumer_orphan(mapc_consumer *r)
+{
+    DeviceGuard g(r->device);
+    mapc::gs_detach(&r->gcopy);
+    mapc::gs_detach(&r->grender);
+    if (r->copy) cudaStreamSynchronize(r->copy);
+    if (r->render) cudaStreamSynchronize(r->render);
+    if (r->producer) {
+        if (r->producer->consumer_fence == r->copy_fence) r->producer->consumer_fence = nullptr;
+        r->producer->consumer = nullptr;
+    }
+    r->producer = nullptr;
+    r->compute_fence = nullptr;
+}
+
 extern "C" {
 
 mapc_status mapc_consumer_destroy(mapc_consumer *r)
@@ -1386,7 +1480,10 @@ mapc_status mapc_consumer_destroy(mapc_consumer *r)
     mapc::gs_detach(&r->grender);
     if (r->copy) cudaStreamSynchronize(r->copy);
     if (r->render) cudaStreamSynchronize(r->render);
-    if (r->producer && r->producer->consumer_fence == r->copy_fence) r->producer->consumer_fence = nullptr;
+    if (r->producer) {
+        if (r->producer->consumer_fence == r->copy_fence) r->producer->consumer_fence = nullptr;
+        if (r->producer->consumer == r) r->producer->consumer = nullptr;
+    }
     for (int i = 0; i < 2; ++i) {
         if (r->local[i]) cudaFree(r->local[i]);
         if (r->host[i]) cudaFreeHost(r->host[i]);
@@ -1423,6 +1520,7 @@ mapc_status mapc_consumer_create(mapc_consumer **out, mapc_compute *producer, in
     if (producer->world != 1)
         return fail(MAPC_ERR_UNSUPPORTED, "the headless consumer attaches to an unsharded Compute");
     if (!producer->has_state) return fail(MAPC_ERR_INVALID_ARGUMENT, "producer has no particle state");
+    if (producer->consumer) return fail(MAPC_ERR_INVALID_ARGUMENT, "producer already has a consumer attached");
     int count = 0;
     MAPC_CUDA(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) return fail(MAPC_ERR_INVALID_ARGUMENT, "device %d out of range", device);
@@ -1468,6 +1566,7 @@ mapc_status mapc_consumer_create(mapc_consumer **out, mapc_compute *producer, in
         g_last_error = keep;
         return st;
     }
+    producer->consumer = r;
     *out = r;
     return MAPC_OK;
 }
@@ -1476,6 +1575,7 @@ mapc_status mapc_consumer_draw(mapc_consumer *r, int num_active_particles, uint6
                                int num_particles_copied)
 {
     if (!r || !inout_fence_value) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!r->producer) return fail(MAPC_ERR_INVALID_ARGUMENT, "the producer of this consumer has been destroyed");
     if (num_active_particles < 0 || (uint32_t)num_active_particles > r->n || num_particles_copied < 0 ||
         (uint32_t)num_particles_copied > r->n)
         return fail(MAPC_ERR_INVALID_ARGUMENT, "particle counts outside [0, %u]", r->n);

@@ -243,8 +243,13 @@ __device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned lo
 // TMA: the source stages are filled by 1-D bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) issued
 // by one thread instead of LDG/STS by all; measured A/B in profiles/ -- it changes nothing, because
 // staging is ~0.02 % of the instruction stream either way.
+// SHFL: the A/B for "broadcast the tile with warp shuffles": each lane reads ONE body of a 32-body
+// group from shared memory and the group is handed round with SHFL.IDX (3 per source) instead of one
+// uniform-address LDS.128 per source.  Same bodies in the same order, so bit-identical; measured
+// slower (profiles/), because the shared-memory broadcast read is already a single instruction per
+// source and the shuffles triple the non-FMA issue slots.  Off by default (MAPC_SHFL=1).
 template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER = false, bool TMA = false,
-          bool MASS_IN_LOOP = false>
+          bool MASS_IN_LOOP = false, bool SHFL = false>
 __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_constant__ StepArgs a)
 {
     constexpr int kLoads = TJ / T;  // staging loads per thread per stage
@@ -348,15 +353,36 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
             const int full = cnt & ~(MAPC_BLOCK_SIZE - 1);  // whole 64-body tiles of this stage
             for (int jb = 0; jb < full; jb += MAPC_BLOCK_SIZE) {
                 constexpr int kU = U;
+                if (SHFL) {
+                    for (int h = 0; h < MAPC_BLOCK_SIZE; h += 32) {
+                        const float4 mine = tile[buf][jb + h + (tid & 31)];
 #pragma unroll kU
-                for (int j = 0; j < MAPC_BLOCK_SIZE; ++j) {
-                    const float4 b = tile[buf][jb + j];
-                    if (ORDER == 2) {
-                        group_interaction<P, MASS_IN_LOOP>(b, nxi, nyi, nzi, ax, ay, az);
-                    } else {
+                        for (int j = 0; j < 32; ++j) {
+                            float4 b;
+                            b.x = __shfl_sync(0xffffffffu, mine.x, j);
+                            b.y = __shfl_sync(0xffffffffu, mine.y, j);
+                            b.z = __shfl_sync(0xffffffffu, mine.z, j);
+                            b.w = 0.f;
+                            if (ORDER == 2) {
+                                group_interaction<P, MASS_IN_LOOP>(b, nxi, nyi, nzi, ax, ay, az);
+                            } else {
 #pragma unroll
-                        for (int p = 0; p < P; ++p)
-                            pair_interaction<MASS_IN_LOOP>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+                                for (int p = 0; p < P; ++p)
+                                    pair_interaction<MASS_IN_LOOP>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll kU
+                    for (int j = 0; j < MAPC_BLOCK_SIZE; ++j) {
+                        const float4 b = tile[buf][jb + j];
+                        if (ORDER == 2) {
+                            group_interaction<P, MASS_IN_LOOP>(b, nxi, nyi, nzi, ax, ay, az);
+                        } else {
+#pragma unroll
+                            for (int p = 0; p < P; ++p)
+                                pair_interaction<MASS_IN_LOOP>(b, nxi[p], nyi[p], nzi[p], ax[p], ay[p], az[p]);
+                        }
                     }
                 }
             }

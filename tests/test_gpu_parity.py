@@ -236,9 +236,13 @@ def test_launch_geometry_does_not_change_bits(mapc, gpu):
                 plan = c.Plan()
                 assert (plan["pairs_per_thread"], plan["threads_per_block"]) == (pairs, threads)
             assert gpu_steps(mapc, p, 2).tobytes() == base.tobytes(), (pairs, threads)
+            os.environ["MAPC_SHFL"] = "1"       # warp-shuffle broadcast instead of the LDS broadcast
+            assert gpu_steps(mapc, p, 2).tobytes() == base.tobytes(), ("SHFL", pairs, threads)
+            os.environ.pop("MAPC_SHFL")
     finally:
         os.environ.pop("MAPC_FUSE", None)
         os.environ.pop("MAPC_TMA", None)
+        os.environ.pop("MAPC_SHFL", None)
         os.environ.pop("MAPC_PLAN_PAIRS", None)
         os.environ.pop("MAPC_PLAN_THREADS", None)
 
@@ -346,6 +350,28 @@ def test_headless_consumer_frame_loop(mapc, oracle, gpu):
                 assert np.abs(pos[:, :3] - ref[:, :3]).max() / scale <= TOL_10, frame
             final = c.Download()
             assert_close(oracle, final, states[6], TOL_10, "producer state after 6 frames")
+
+
+def test_producer_destroyed_before_its_consumer(mapc, gpu):
+    """Teardown in the 'wrong' order must not touch freed memory: the orphaned consumer keeps its last
+    completed frame, refuses to draw, and a second consumer on one producer is refused."""
+    n = 1024
+    p = gentle_sphere(mapc, n, seed=6)
+    c = mapc.Compute(n, 0)
+    c.Upload(p)
+    r = mapc.Consumer(c, 0)
+    with pytest.raises(mapc.MapcError):
+        mapc.Consumer(c, 0)
+    for _ in range(3):
+        fence = r.Draw(n, c.GetFenceValue(), n)
+        c.Simulate(n, fence)
+    fence = r.Draw(n, c.GetFenceValue(), n)     # copy stream now gated on a Simulate that never comes
+    c.close()
+    with pytest.raises(mapc.MapcError):
+        r.Draw(n, 1, n)
+    frame, pos = r.Latest()
+    assert frame >= 0 and pos.shape == (n, 4) and np.isfinite(pos).all()
+    r.close()
 
 
 def test_batched_steps_equal_single_steps(mapc, gpu):
