@@ -1,6 +1,7 @@
 /*
- * oracle/oracle.c -- see oracle.h.  TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (no reference
- * fixtures exist for this path; pinned by closed-form KATs + fp64 direct sum).
+ * oracle/oracle.c -- see oracle.h.  TEST INFRASTRUCTURE ONLY.  Pinned bit for bit against the
+ * reference's own shader code compiled for the CPU (oracle/_ref, tests/test_reference_shader.py),
+ * plus closed-form KATs and an fp64 direct sum.
  *
  * Build: gcc -O3 -march=x86-64-v3 -ffp-contract=off -fopenmp -fPIC -shared (oracle/Makefile).
  * -ffp-contract=off matters: the LITERAL flavour must keep every mul and add separate, and

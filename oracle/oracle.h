@@ -5,12 +5,19 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load it, and only as the checker / reported CPU baseline.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
- * this path and its shader (HLSL cs_5_0 run by D3D12 on
- * Windows, Particles/Compute.cpp:488-511) cannot execute here, so there is no
- * reference output to pin this restatement against.  It is pinned instead by
- * closed-form known-answer tests derived from Particles/nBodyGravityCS.hlsl:44-57
- * and :86-109 (tests/test_oracle_kat.py) and by an fp64 direct sum.
+ * PARITY PINNED AGAINST THE REFERENCE'S OWN CODE.  The reference ships no tests, golden
+ * vectors or fixtures for this path and runs its shader as HLSL
+ * cs_5_0 through D3D12 on Windows (Particles/Compute.cpp:488-511), which cannot execute
+ * here.  But the shader source itself compiles with g++ behind a small type shim: the
+ * Makefile builds Particles/nBodyGravityCS.hlsl, unmodified in every arithmetic line, into
+ * oracle/_ref/libref_shader.so (hlsl_shim.hpp, lower_hlsl.py, ref_harness.cpp), and the
+ * LITERAL flavour below reproduces its bodyBodyInteraction, its CSMain and all-pairs steps
+ * built from them BIT FOR BIT (tests/test_reference_shader.py; outputs committed as
+ * tests/golden/ref_shader_vectors.npz so the pin travels without /root/reference).
+ * What that pin cannot cover is how a D3D12 driver rounds the same HLSL (mad contraction,
+ * rsq approximation): that latitude is what the 1e-5 tolerance is for.  Further pins:
+ * closed-form known-answer tests (tests/test_oracle_kat.py), an independent numpy-float32
+ * transcription (tests/test_oracle_numpy.py) and an fp64 direct sum.
  *
  * What it follows (all paths relative to /root/reference):
  *   Particles/nBodyGravityCS.hlsl:37-38   softeningSquared = 25, g_fParticleMass = 70000

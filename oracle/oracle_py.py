@@ -1,8 +1,9 @@
 """ctypes face of oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY (see oracle/oracle.h).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
-import this module.  PARITY UNPINNED: the reference has no fixtures for this path; the oracle is
-pinned by closed-form KATs (tests/test_oracle_kat.py) and an fp64 direct sum.
+import this module.  The LITERAL flavour is pinned bit for bit against the reference's own shader code
+compiled for the CPU (oracle/ref_shader.py, tests/test_reference_shader.py), and by closed-form KATs
+(tests/test_oracle_kat.py), a numpy transcription and an fp64 direct sum.
 """
 from __future__ import annotations
 

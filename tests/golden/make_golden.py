@@ -1,7 +1,8 @@
 """Generates the golden fixtures in tests/golden/ from the CPU oracle (LITERAL flavour).
 
-The reference has no fixtures and cannot run here (HLSL / D3D12), so these vectors pin the
-oracle against silent drift and give the GPU parity tests a committed target.
+The reference has no fixtures of its own; these vectors pin the oracle against silent drift and give
+the GPU parity tests a committed target.  (Vectors produced by the reference's own shader code are in
+ref_shader_vectors.npz, see make_ref_shader_vectors.py.)
 Usage: python tests/golden/make_golden.py
 """
 import importlib

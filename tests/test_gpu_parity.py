@@ -101,6 +101,22 @@ def test_golden_allpairs(mapc, oracle, gpu, name):
     assert np.abs(acc_gpu - g["accel_fp64"]).max() / scale < 1e-4
 
 
+def test_against_reference_shader_vectors(mapc, oracle, gpu):
+    """The CUDA path against outputs of the REFERENCE's own shader code (nBodyGravityCS.hlsl compiled for
+    the CPU, tests/golden/make_ref_shader_vectors.py): all-pairs through its bodyBodyInteraction, and the
+    shipped CSMain (gravity well)."""
+    g = np.load(os.path.join(GOLDEN, "ref_shader_vectors.npz"))
+    for case, dt, damping in (("a", 0.1, 1.0), ("b", 0.05, 0.995)):
+        inp = g[f"allpairs_{case}_in"].view(mapc.POSVELO_DTYPE).reshape(-1)
+        assert int(g[f"allpairs_{case}_S"]) == mapc.plan_segments(inp.shape[0])
+        got = gpu_steps(mapc, inp, 1, dt=dt, damping=damping)
+        assert_close(oracle, got, g[f"allpairs_{case}_out"], TOL_1, f"reference shader all-pairs {case}")
+    w = g["well_in"].view(mapc.POSVELO_DTYPE).reshape(-1)
+    assert_close(oracle, gpu_steps(mapc, w, 1, mode=mapc.FORCE_WELL), g["well_out_a"], 2e-6, "reference CSMain")
+    assert_close(oracle, gpu_steps(mapc, w, 1, dt=0.05, damping=0.995, mode=mapc.FORCE_WELL), g["well_out_b"],
+                 2e-6, "reference CSMain, dt=0.05 damping=0.995")
+
+
 def test_golden_well(mapc, oracle, gpu):
     g = np.load(os.path.join(GOLDEN, "well_1000.npz"))
     inp = g["input"].view(mapc.POSVELO_DTYPE).reshape(-1)

@@ -1,7 +1,8 @@
 """Known-answer tests that pin the CPU oracle.
 
-The reference ships no fixtures for this path ("parity unpinned"), so each expected value is
-derived by hand from Particles/nBodyGravityCS.hlsl:44-57 (pair) and :86-109 (CSMain).
+The reference ships no fixtures for this path, so each expected value here is derived by hand from
+Particles/nBodyGravityCS.hlsl:44-57 (pair) and :86-109 (CSMain); tests/test_reference_shader.py pins the
+oracle against the shader's own code compiled for the CPU.
 """
 import numpy as np
 import pytest

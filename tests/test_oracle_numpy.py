@@ -3,8 +3,8 @@
 numpy's float32 add / sub / mul / div / sqrt are IEEE-754 correctly rounded, exactly like the C
 operators under -ffp-contract=off, so a line-by-line transcription of
 Particles/nBodyGravityCS.hlsl:44-57 and :86-109 must give the same bits as oracle/oracle.c (LITERAL
-flavour).  Two restatements written separately and agreeing on every bit is the strongest pin
-available without the reference's own runtime (HLSL/D3D12 cannot execute here: "parity unpinned").
+flavour).  Two restatements written separately and agreeing on every bit complement the direct pin
+against the reference's shader code compiled for the CPU (tests/test_reference_shader.py).
 """
 import numpy as np
 import pytest
