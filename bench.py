@@ -164,7 +164,9 @@ def cpu_implementations(n: int):
     arithmetic bit for bit (tests/test_reference_shader.py) vectorised 8 targets wide."""
     orc = importlib.import_module("oracle.oracle_py")
     orc.load()
-    threads = orc.max_threads()
+    # every core this process may run on, passed explicitly (num_threads clause): torchrun exports
+    # OMP_NUM_THREADS=1, which would otherwise turn the CPU arm into a single-thread run
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     S = orc.default_segments(n)
     out = []
     refsh = importlib.import_module("oracle.ref_shader")
