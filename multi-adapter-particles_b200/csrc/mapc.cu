@@ -401,7 +401,7 @@ Switches read_switches()
 // target lanes the last block leaves idle.  The shape changes neither the arithmetic nor its order
 // (only S does), so it is free to vary with N, the shard size and the device.
 struct Shape { int pairs, threads; float efficiency; };
-constexpr Shape kShapes[6] = {{4, 256, 0.763f}, {4, 128, 0.753f}, {2, 128, 0.734f},
+constexpr Shape kShapes[6] = {{4, 256, 0.763f}, {4, 128, 0.753f}, {2, 128, 0.754f},
                               {2, 64, 0.734f},  {1, 64, 0.728f},  {1, 32, 0.722f}};
 
 Plan make_plan(int n_targets, int n_sources, int sm_count, const Switches &sw)
@@ -583,9 +583,12 @@ mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::Step
         if (shfl) return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false, kAlt>(c, args, stream); \
         return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false>(c, args, stream);             \
     }
+    // unroll / order / blocks-per-SM per shape from the fused kernel measured in the library at N = 262,144
+    // (the unfused tools/ubench sweep ranks (4,256) U=2 op-major first, 77.3 %, but fused it is 24.67 ms
+    // against 24.04 ms for U=8 pair-major; profiles/r01_ubench_shapes_11op.txt, r01_shapes_in_library.txt)
     MAPC_SHAPE(4, 256, 256, 8, 2, 0, true)
     MAPC_SHAPE(4, 128, 256, 8, 4, 0, true)
-    MAPC_SHAPE(2, 128, 256, 4, 4, 2, true)
+    MAPC_SHAPE(2, 128, 256, 1, 8, 2, true)
     MAPC_SHAPE(2, 64, 64, 4, 8, 2, false)
     MAPC_SHAPE(1, 64, 64, 8, 16, 0, false)
     MAPC_SHAPE(1, 32, 64, 8, 32, 0, false)
