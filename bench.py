@@ -67,12 +67,13 @@ def read_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "_source": "fallback (B200_PROFILING.md)"}
 
 
-def ncu_traffic(n: int, world: int):
+def ncu_traffic(n: int, world: int, segments: int):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the force kernel from the committed
     `ncu --set full` capture (profiles/ncu_traffic.json); null when the workload differs from it."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        return float(t["dram_bytes_per_launch"]) if world == 1 and int(t["n"]) == n else None
+        same = world == 1 and int(t["n"]) == n and int(t.get("segments", -1)) == segments
+        return float(t["dram_bytes_per_launch"]) if same else None
     except Exception:
         return None
 
@@ -338,7 +339,10 @@ def run_mapc(args) -> None:
     achieved_tflops = per_rank_interactions * FLOP_PER_INTERACTION / (event_ms * 1e-3) / 1e12
     probe_packed, _ = pkg.fp32_peak_probe(local_rank, True)
     probe_scalar, _ = pkg.fp32_peak_probe(local_rank, False)
-    hbm_bytes = 80.0 * c.num_local                   # 64 B PosVelo r/w + 16 B packed mirror per body
+    # per body: 64 B PosVelo r/w + 16 B packed mirror, plus one 16 B partial per canonical segment written by
+    # the cell that computed it and read back by the combine (these mostly stay in the 126 MB L2)
+    segments = int(c.Plan()["segments"])
+    hbm_bytes = (80.0 + 32.0 * segments) * c.num_local
     roofline = {
         "bound": "fp32_fma", "kernel": "force_cells_kernel (force + fused combine/integrate: the whole step is this one kernel)",
         "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
@@ -346,7 +350,7 @@ def run_mapc(args) -> None:
                     f"{FLOP_PER_INTERACTION:.0f} flop/interaction",
         "peak_probe_ffma2_tflops": probe_packed, "peak_probe_ffma_tflops": probe_scalar,
         "frac_of_probe": achieved_tflops / max(probe_packed, probe_scalar),
-        "kernel_ms": event_ms, "kernel_ms_in_kernel_stamps": kernel_ms, "traffic": ncu_traffic(n, world),
+        "kernel_ms": event_ms, "kernel_ms_in_kernel_stamps": kernel_ms, "traffic": ncu_traffic(n, world, segments),
         "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes / (event_ms * 1e-3) / 1e9,
                 "peak_gbs": peaks.get("hbm_gbs"), "note": "negligible: the step is FMA-pipe bound"},
     }

@@ -42,7 +42,7 @@ extern "C" {
 #define MAPC_PARTICLE_SPREAD        400.0f     /* Particles/defines.h:42                       */
 #define MAPC_MIN_NUM_PARTICLES      (256 * 1024)       /* Particles/defines.h:44               */
 #define MAPC_MAX_NUM_PARTICLES      (4 * 1024 * 1024)  /* Particles/defines.h:45               */
-#define MAPC_MAX_SEGMENTS           64
+#define MAPC_MAX_SEGMENTS           128
 #define MAPC_NCCL_UNIQUE_ID_BYTES   128
 #define MAPC_IPC_BLOB_BYTES         256
 
@@ -257,9 +257,11 @@ MAPC_API mapc_status mapc_consumer_counters(const mapc_consumer *r, uint64_t out
 MAPC_API mapc_status mapc_consumer_wait_for_gpu(mapc_consumer *r);
 
 /* ---- plan / diagnostics -------------------------------------------------------------------- */
-/* canonical number of j segments for n sources: 32 below 131072 sources; from there 8, doubling up to
- * 64 so that no segment exceeds 65,536 sources (bounds the fp32 accumulation error).  The partial sums
- * of the segments are combined left to right, independent of the GPU count. */
+/* canonical number of j segments for n sources: 32 up to 262,144 sources, then 64 (up to 524,288) and
+ * 128: each segment is one sequential fp32 accumulation chain, and chains of at most 8,192 terms keep
+ * the rounding noise of the sum well inside the 1e-5 parity tolerance (with 32,768-term chains two
+ * correctly rounded fp32 implementations already differ by 1.07e-5 at N = 262,144).  The partial sums of
+ * the segments are combined left to right, independent of the GPU count. */
 MAPC_API int mapc_plan_segments(uint32_t n_sources);
 /* number of this library's kernels launched by the handle so far */
 MAPC_API uint64_t mapc_compute_kernel_launches(const mapc_compute *c);

@@ -720,15 +720,17 @@ mapc_status mapc_device_count(int *count)
 }
 
 // Canonical segment count: a function of the number of sources only (never of the GPU count or the
-// launch shape).  Small problems get 32 segments for parallelism; large ones keep every segment's
-// fp32 accumulation chain at <= 65,536 terms (8 segments up to 524,288 sources, then 16, 32, 64):
-// a sequential fp32 sum of 524,288 terms is ~1e-5 away from the fp64 sum -- the size of the parity
-// tolerance itself -- while 65,536-term chains stay near 1e-6.
+// launch shape).  Every segment is one sequential fp32 accumulation chain per target, so its length
+// sets the rounding noise of the sum: once a close neighbour has made the accumulator large, every later
+// term is rounded at that magnitude.  Measured at N = 262,144 over all targets, two correctly rounded CPU
+// evaluations of the same formula (oracle LITERAL vs MIRRORED) differ by 1.07e-5 with 32,768-term chains
+// (S = 8) -- the size of the parity tolerance itself -- and by 4.6e-6 with 8,192-term chains (S = 32).
+// So: 32 segments (also what small problems want for parallelism) while chains stay <= 8,192 terms,
+// then 64 and 128.
 int mapc_plan_segments(uint32_t n_sources)
 {
-    if (n_sources < 131072u) return 32;
-    int s = 8;
-    while (s < MAPC_MAX_SEGMENTS && (uint64_t)s * 65536u < n_sources) s *= 2;
+    int s = 32;
+    while (s < MAPC_MAX_SEGMENTS && (uint64_t)s * 8192u < n_sources) s *= 2;
     return s;
 }
 

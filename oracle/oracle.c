@@ -32,9 +32,8 @@ int mapo_num_tiles(int n) { return (n + MAPO_TILE - 1) / MAPO_TILE; }
 
 int mapo_default_segments(int n)
 {
-    if (n < 131072) return 32;
-    int s = 8;
-    while (s < 64 && (long long)s * 65536 < n) s *= 2;   /* chains of at most 65,536 terms */
+    int s = 32;
+    while (s < 128 && (long long)s * 8192 < n) s *= 2;   /* chains of at most 8,192 terms while s < 128 */
     return s;
 }
 

@@ -51,8 +51,8 @@ enum { MAPO_LITERAL = 0, MAPO_MIRRORED = 1 };
 
 /* dimx of Compute.cpp:544 */
 int  mapo_num_tiles(int n);
-/* canonical segment count for n sources: 32 below 131072; from there 8, doubling (up to 64) so that
- * no segment exceeds 65,536 sources */
+/* canonical segment count for n sources: 32, doubling (up to 128) so that no segment exceeds 8,192
+ * sources: bounds the rounding noise of the sequential fp32 chains (see mapc_plan_segments) */
 int  mapo_default_segments(int n);
 /* j range [j0, j1) of segment s out of S over n_sources sources */
 void mapo_segment_range(int n_sources, int S, int s, int *j0, int *j1);

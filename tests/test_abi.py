@@ -42,11 +42,11 @@ def test_constants_match_reference(mapc):
 
 
 def test_plan_segments_matches_oracle_rule(mapc, oracle):
-    for n in (1, 64, 1000, 10_000, 131_071, 131_072, 262_144, 524_288, 524_289, 741_376, 1_048_576, 2_097_153,
-              4_194_304, 8_000_000):
+    for n in (1, 64, 1000, 10_000, 131_071, 131_072, 262_144, 262_145, 524_288, 524_289, 741_376, 1_048_576,
+              2_097_153, 4_194_304, 8_000_000):
         assert mapc.plan_segments(n) == oracle.default_segments(n)
-    assert [mapc.plan_segments(n) for n in (10_000, 262_144, 524_288, 741_376, 1_048_576, 4_194_304)] == \
-        [32, 8, 8, 16, 16, 64]
+    assert [mapc.plan_segments(n) for n in (10_000, 262_144, 370_688, 524_288, 741_376, 1_048_576, 4_194_304)] == \
+        [32, 32, 64, 64, 128, 128, 128]
 
 
 def test_no_cpu_fallback(mapc):
@@ -114,7 +114,7 @@ int main(void) {
     mapc_posvelo p; mapc_shared_handles h; mapc_compute *c = 0;
     memset(&p, 0, sizeof p); memset(&h, 0, sizeof h);
     if (sizeof(mapc_posvelo) != 32) return 2;
-    if (mapc_plan_segments(262144u) != 8 || mapc_plan_segments(10000u) != 32) return 3;
+    if (mapc_plan_segments(262144u) != 32 || mapc_plan_segments(4194304u) != MAPC_MAX_SEGMENTS) return 3;
     if (mapc_compute_create(&c, 0u, 0, 0) != MAPC_ERR_INVALID_ARGUMENT) return 4;
     if (strstr(mapc_last_error(), "num_particles") == 0) return 5;
     printf("%s\n", mapc_version());
