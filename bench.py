@@ -78,6 +78,15 @@ def ncu_traffic(n: int, world: int, segments: int):
         return None
 
 
+def ncu_capture_info():
+    """What the committed capture was taken on (so a null `traffic` can be read against it)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return {k: t.get(k) for k in ("n", "segments", "dram_bytes_per_launch", "source")}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -339,10 +348,12 @@ def run_mapc(args) -> None:
     achieved_tflops = per_rank_interactions * FLOP_PER_INTERACTION / (event_ms * 1e-3) / 1e12
     probe_packed, _ = pkg.fp32_peak_probe(local_rank, True)
     probe_scalar, _ = pkg.fp32_peak_probe(local_rank, False)
-    # per body: 64 B PosVelo r/w + 16 B packed mirror, plus one 16 B partial per canonical segment written by
-    # the cell that computed it and read back by the combine (these mostly stay in the 126 MB L2)
+    # algorithmic HBM bytes per body: 64 B PosVelo read + write and the 16 B packed mirror.  The implementation
+    # also writes one 16 B partial per (target, canonical segment) and reads it back in the combine; that
+    # scratch is reported separately (it mostly lives in the 126 MB L2 and is noise next to the FMA time).
     segments = int(c.Plan()["segments"])
-    hbm_bytes = (80.0 + 32.0 * segments) * c.num_local
+    hbm_bytes = 80.0 * c.num_local
+    scratch_bytes = 32.0 * segments * c.num_local
     roofline = {
         "bound": "fp32_fma", "kernel": "force_cells_kernel (force + fused combine/integrate: the whole step is this one kernel)",
         "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
@@ -351,7 +362,10 @@ def run_mapc(args) -> None:
         "peak_probe_ffma2_tflops": probe_packed, "peak_probe_ffma_tflops": probe_scalar,
         "frac_of_probe": achieved_tflops / max(probe_packed, probe_scalar),
         "kernel_ms": event_ms, "kernel_ms_in_kernel_stamps": kernel_ms, "traffic": ncu_traffic(n, world, segments),
+        "traffic_capture": ncu_capture_info(),
         "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes / (event_ms * 1e-3) / 1e9,
+                "partials_scratch_bytes_per_step": scratch_bytes,
+                "with_scratch_gbs": (hbm_bytes + scratch_bytes) / (event_ms * 1e-3) / 1e9,
                 "peak_gbs": peaks.get("hbm_gbs"), "note": "negligible: the step is FMA-pipe bound"},
     }
 

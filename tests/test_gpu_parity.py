@@ -336,22 +336,6 @@ def test_full_size_262144_properties_and_subsampled_parity(mapc, oracle, gpu):
     assert gpu_steps(mapc, p, 1).tobytes() == got.tobytes()
 
 
-def test_full_size_262144_full_oracle_parity(mapc, oracle, gpu):
-    """BASELINE config 3, ALL 262,144 targets against the LITERAL oracle (6.9e10 interactions per step on the
-    host cores: seconds with the vectorised oracle): one step on the bench workload at 1e-5, and ten steps
-    on a close-pair-free lattice sphere of the same size at 1e-4."""
-    p = mapc.ic.workload("sphere_262144")
-    n = p.shape[0]
-    assert_close(oracle, gpu_steps(mapc, p, 1), oracle.step_allpairs(p, flavour=oracle.LITERAL), TOL_1,
-                 "N=262,144, all targets, 1 step")
-    q = mapc.ic.lattice_sphere(n, 8000.0, seed=12, speed=1.0)
-    got = gpu_steps(mapc, q, 10)
-    ref = q
-    for _ in range(10):
-        ref = oracle.step_allpairs(ref, flavour=oracle.LITERAL)
-    assert_close(oracle, got, ref, TOL_10, "N=262,144 lattice, all targets, 10 steps")
-
-
 def test_headless_consumer_frame_loop(mapc, oracle, gpu):
     """Particles::Draw's loop (Particles.cpp:446-448) with the headless consumer: frame k dumps the
     result of step k-1 (one-frame latency), the producer never overwrites a side the copy still
