@@ -21,7 +21,8 @@ def shard_range(n: int, rank: int, world: int):
 
 def weak_scaled_n(world: int, base: int = BASE_N) -> int:
     """N that keeps the per-GPU work (N^2 / world pairs) of the base workload: base * sqrt(world),
-    rounded to a multiple of 64 * 8 * world so shards and the 8 canonical segments stay tile aligned."""
+    rounded to a multiple of 64 * 8 * world: shards are then whole tiles, and because the canonical segment
+    count (32/64/128) is a multiple of every supported world size no segment straddles two shards."""
     if world == 1:
         return base
     q = TILE * 8 * world
