@@ -92,3 +92,46 @@ def test_local_segment_classification(mapc):
     for s in range(32):
         a, b = d.segment_range(10_000, 32, s)
         assert (a, b) == tuple(__import__("oracle.oracle_py", fromlist=["x"]).segment_range(10_000, 32, s))
+
+
+def test_canonical_segments_partition_the_sources(mapc, oracle):
+    """Properties of the canonical segmentation that every size must satisfy: the S ranges tile [0, n)
+    exactly, in order, on 64-body boundaries (only the last may be ragged), the three statements of the rule
+    (library, oracle, host helper) agree, and no chain is longer than 8,192 sources while S < 128."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(min_value=1, max_value=5_000_000))
+    def check(n):
+        S = mapc.plan_segments(n)
+        assert S == oracle.default_segments(n) and S in (32, 64, 128)
+        edge, longest = 0, 0
+        for s in range(S):
+            a, b = mapc.dist.segment_range(n, S, s)
+            assert (a, b) == oracle.segment_range(n, S, s)
+            assert a == edge and b >= a and (b % 64 == 0 or b == n)
+            edge, longest = b, max(longest, b - a)
+        assert edge == n
+        if n <= 128 * 8192:
+            assert longest <= 8192 + 64       # +64: a boundary is rounded down to a whole tile
+    check()
+
+
+def test_no_canonical_segment_straddles_a_shard(mapc):
+    """The bench's multi-GPU sizes (weak-scaled and BASELINE configs 4 and 5): with S a multiple of the world
+    size every segment lies inside one rank's shard, so the peer exchange never needs a gathered copy and the
+    local/remote split of the NCCL path is exact."""
+    d = mapc.dist
+    sizes = [d.weak_scaled_n(w) for w in (2, 4, 8)] + [1_048_576, 4_194_304]
+    for n in sizes:
+        S = mapc.plan_segments(n)
+        for world in (2, 4, 8):
+            if n % (64 * world):
+                continue
+            count = n // world
+            owned = []
+            for r in range(world):
+                loc = d.local_segments(n, S, r * count, count)
+                assert len(loc) == S // world, (n, world, r, loc)
+                owned += loc
+            assert sorted(owned) == list(range(S))
