@@ -586,12 +586,7 @@ mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::Step
     // unroll / order / blocks-per-SM per shape from the fused kernel measured in the library at N = 262,144
     // (the unfused tools/ubench sweep ranks (4,256) U=2 op-major first, 77.3 %, but fused it is 24.67 ms
     // against 24.04 ms for U=8 pair-major; profiles/r01_ubench_shapes_11op.txt, r01_shapes_in_library.txt)
-    MAPC_SHAPE(4, 256, 256, 8, 2, 0, true)
-    MAPC_SHAPE(4, 128, 256, 8, 4, 0, true)
-    MAPC_SHAPE(2, 128, 256, 1, 8, 2, true)
-    MAPC_SHAPE(2, 64, 64, 4, 8, 2, false)
-    MAPC_SHAPE(1, 64, 64, 8, 16, 0, false)
-    MAPC_SHAPE(1, 32, 64, 8, 32, 0, false)
+#include "force_shapes.inc"
 #undef MAPC_SHAPE
     return fail(MAPC_ERR_INVALID_ARGUMENT, "no kernel for launch shape P=%d T=%d", pl.pairs, pl.threads);
 }

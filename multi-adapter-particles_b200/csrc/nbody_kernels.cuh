@@ -19,7 +19,15 @@
 //  * No tensor cores: the work is not a contraction (d^2 via a GEMM cancels catastrophically).
 #pragma once
 
+// MAPC_HOST_EMULATION (tests/emu/ only, never defined by the product build): the same kernel source
+// compiled by g++ over a thread-per-CUDA-thread shim, so the CPU suite can check the kernels' indexing,
+// staging, tails and fused combine bit for bit against the oracle without a GPU.  The PTX below then has
+// host stand-ins (tests/emu/cuda_emu.hpp); nothing else in this file knows about it.
+#ifdef MAPC_HOST_EMULATION
+#include "cuda_emu.hpp"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "../../include/mapc.h"
@@ -46,12 +54,14 @@ __host__ __device__ inline void segment_range(int n_sources, int S, int s, int &
     j1 = (int)b;
 }
 
+#ifndef MAPC_HOST_EMULATION
 __device__ __forceinline__ float rsqrt_approx(float x)
 {
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+#endif
 
 // Two bodyBodyInteraction calls (nBodyGravityCS.hlsl:44-57) at once: lanes .x/.y are two
 // target bodies, b is the source body.  Operation order per lane:
@@ -186,6 +196,7 @@ struct StepArgs {
     unsigned long long fence_value;
 };
 
+#ifndef MAPC_HOST_EMULATION
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
     unsigned long long t;
@@ -227,6 +238,12 @@ __device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned lo
     return v;
 }
 
+// programmatic dependent launch (no-ops for a launch without the programmatic-serialization attribute)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbarrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#endif  // !MAPC_HOST_EMULATION
+
 // Force kernel.  Work is cut into cells = (target block of T*2P bodies) x (canonical segment); one
 // thread block evaluates one cell: blockIdx.x = target block, blockIdx.y = index into args.segs.  (A
 // persistent variant that walked several cells per block was measured 25 % slower: with the targets
@@ -263,7 +280,7 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
         if (tid == 0) {
             mbar_init(&full_bar[0], 1);
             mbar_init(&full_bar[1], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            fence_mbarrier_init();
         }
         __syncthreads();
     }
@@ -272,8 +289,8 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
     // Programmatic dependent launch (batched steps): let the next step's grid start filling SMs as this
     // one drains, and do not touch the previous step's output before that grid has completely finished.
     // Both are no-ops for a launch without the programmatic-serialization attribute.
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_launch_dependents();
+    pdl_wait();
     if (FUSE && a.stamp_begin != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
         *a.stamp_begin = global_timer_ns();
     if (PEER) {

@@ -1,0 +1,213 @@
+// tests/emu/emu_kernels.cpp -- TEST INFRASTRUCTURE ONLY.  Compiles csrc/nbody_kernels.cuh -- the product's
+// kernel source, unchanged -- for the host over tests/emu/cuda_emu.hpp and drives it the way
+// csrc/mapc.cu's enqueue_one does: same StepArgs, same segment lists (local cells first, remote cells in a
+// second launch, shared arrival counters), same shape table (csrc/force_shapes.inc), same unfused
+// integrate_kernel alternative, optionally `world` emulated ranks with the NCCL-style layout (every rank
+// sees all N packed positions) or the peer layout (a rank's packed array is valid only inside its own
+// shard, everything else is poisoned with NaN, and remote cells must go through seg_src[]).
+// The Python side (tests/test_kernel_emulation.py) compares the result bit for bit with the oracle's
+// MIRRORED flavour.  Built by tests/emu/Makefile with g++ -ffp-contract=off; never linked into libmapc.so.
+#define MAPC_HOST_EMULATION 1
+#include "../../multi-adapter-particles_b200/csrc/nbody_kernels.cuh"
+
+#include <sched.h>
+
+#include <cstring>
+#include <limits>
+#include <vector>
+
+namespace cuda_emu {
+thread_local uint3 t_threadIdx, t_blockIdx;
+thread_local dim3 t_blockDim, t_gridDim;
+thread_local Block *t_block = nullptr;
+}  // namespace cuda_emu
+
+namespace {
+
+using mapc::StepArgs;
+
+template <int P, int T, int TJ, int U, int MINB, int ORDER>
+void launch_shape(bool fuse, bool peer, bool inloop, const StepArgs &a, int order)
+{
+    const dim3 grid((unsigned)a.n_iblocks, (unsigned)a.segs.count, 1), block(T, 1, 1);
+    if (a.segs.count == 0 || a.i_cnt <= 0) return;
+    // the instantiations csrc/mapc.cu launches (TMA and SHFL staging are hardware A/Bs, not emulated)
+    if (fuse && peer) cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, true>(a); });
+    else if (fuse && inloop) cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, false, false, true>(a); });
+    else if (fuse) cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, false>(a); });
+    else cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, false, false>(a); });
+}
+
+bool launch_force(int pairs, int threads, bool fuse, bool peer, bool inloop, const StepArgs &a, int order)
+{
+#define MAPC_SHAPE(P, T, TJ, U, MINB, ORDER, HAS_TMA)                 \
+    if (pairs == P && threads == T) {                                 \
+        launch_shape<P, T, TJ, U, MINB, ORDER>(fuse, peer, inloop, a, order); \
+        return true;                                                  \
+    }
+#include "../../multi-adapter-particles_b200/csrc/force_shapes.inc"
+#undef MAPC_SHAPE
+    return false;
+}
+
+// csrc/mapc.cu local_targets(): Dispatch(ceil(n_active/64)) groups of 64, clipped to the shard
+int local_targets(int n, int i_first, int n_local, int n_active)
+{
+    if (n_active <= 0) return 0;
+    long long t = ((long long)n_active + MAPC_BLOCK_SIZE - 1) / MAPC_BLOCK_SIZE * MAPC_BLOCK_SIZE;
+    if (t > n) t = n;
+    long long loc = t - i_first;
+    if (loc < 0) loc = 0;
+    if (loc > n_local) loc = n_local;
+    return (int)loc;
+}
+
+struct alignas(16) PV { float pos[4]; float velo[4]; };
+static_assert(sizeof(PV) == sizeof(mapc_posvelo), "PosVelo layout");
+
+}  // namespace
+
+extern "C" {
+
+// One all-pairs step.  in/out: n PosVelo each (out must hold the previous contents of the written side: bodies
+// that are not targets keep them).  pos_next_out: n float4, the packed mirror of the written side as rank 0
+// .. world-1 wrote it (own shards only).  info[0] = kernel launches, info[1] = fence word after the step,
+// info[2] = 1 if every arrival counter and the `done` counter were back at zero.
+// returns 0, or -1 for an unknown shape, -2 for a layout the library would refuse (peer with straddling segments)
+int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next_out, int n, int n_active,
+                      float dt, float damping, int S, int pairs, int threads, int fuse, int mass_in_loop,
+                      int world, int peer, int block_order, unsigned long long *info)
+{
+    if (n % world) return -2;
+    const int n_local = n / world;
+    const int n_sources = n_active;
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    unsigned long long launches = 0, fence_word = 0;
+    bool counters_clean = true;
+
+    // read-side packed positions per rank
+    std::vector<std::vector<float4>> packed(world, std::vector<float4>(n));
+    for (int r = 0; r < world; ++r)
+        for (int i = 0; i < n; ++i) {
+            const bool own = i >= r * n_local && i < (r + 1) * n_local;
+            if (peer && world > 1 && !own) packed[r][i] = make_float4(nan, nan, nan, nan);
+            else packed[r][i] = make_float4(in[i].pos[0], in[i].pos[1], in[i].pos[2], in[i].pos[3]);
+        }
+    std::vector<unsigned long long> flags(world, 7);   // every owner has published step 7
+
+    for (int r = 0; r < world; ++r) {
+        const int i_first = r * n_local;
+        const int n_targets = local_targets(n, i_first, n_local, n_active);
+        if (n_targets <= 0) continue;
+        const int per_block = threads * 2 * pairs;
+        std::vector<PV> in_local(n_local), out_local(n_local);
+        std::memcpy(in_local.data(), in + i_first, (size_t)n_local * sizeof(PV));
+        std::memcpy(out_local.data(), out + i_first, (size_t)n_local * sizeof(PV));
+        std::vector<float4> partial((size_t)S * n_local, make_float4(nan, nan, nan, nan));
+        std::vector<float4> pos_next(n, make_float4(nan, nan, nan, nan));
+        std::vector<unsigned> counters(n_local / 64 + 2, 0u);
+        unsigned done = 0;
+        unsigned long long stamps[2] = {0, 0};
+
+        StepArgs a{};
+        a.pos = packed[r].data();
+        a.partial = partial.data();
+        a.partial_stride = n_local;
+        a.i_first = i_first;
+        a.i_cnt = n_targets;
+        a.n_sources = n_sources;
+        a.S = S;
+        a.n_iblocks = (n_targets + per_block - 1) / per_block;
+        a.counters = counters.data();
+        a.in = reinterpret_cast<const mapc_posvelo *>(in_local.data());
+        a.out = reinterpret_cast<mapc_posvelo *>(out_local.data());
+        a.pos_next = pos_next.data();
+        a.dt = dt;
+        a.damping = damping;
+        a.done = &done;
+        a.stamp_begin = fuse ? &stamps[0] : nullptr;
+        a.stamp_end = fuse ? &stamps[1] : nullptr;
+        a.fence_word = (fuse && world == 1) ? &fence_word : nullptr;
+        a.fence_value = 42;
+
+        mapc::SegList local{0, {}}, remote{0, {}};
+        int owner[MAPC_MAX_SEGMENTS];
+        bool peer_ok = peer && fuse && n_sources == n && !mass_in_loop;
+        for (int s = 0; s < S; ++s) {
+            int j0, j1;
+            mapc::segment_range(n_sources, S, s, j0, j1);
+            const bool inside = j0 >= i_first && j1 <= i_first + n_local;
+            owner[s] = j1 > j0 ? j0 / n_local : r;
+            if (j1 > j0 && (j1 - 1) / n_local != owner[s]) peer_ok = false;
+            const bool is_local = world == 1 || inside;
+            (is_local ? local : remote).ids[(is_local ? local : remote).count++] = s;
+        }
+        if (peer && world > 1 && !peer_ok && remote.count > 0) return -2;
+
+        a.segs = local;
+        if (!launch_force(pairs, threads, fuse, false, mass_in_loop, a, block_order)) return -1;
+        launches += (local.count > 0);
+        if (local.count > 0) a.stamp_begin = nullptr;
+        if (remote.count > 0) {
+            a.segs = remote;
+            const bool use_peer = peer_ok && world > 1;
+            if (use_peer) {
+                for (int k = 0; k < remote.count; ++k) {
+                    a.seg_src[k] = packed[owner[remote.ids[k]]].data();
+                    a.seg_flag[k] = &flags[owner[remote.ids[k]]];
+                }
+                a.flag_expect = 7;
+            }
+            if (!launch_force(pairs, threads, fuse, use_peer, mass_in_loop, a, block_order)) return -1;
+            ++launches;
+        }
+        if (!fuse) {
+            // MAPC_FUSE=0: the separate combine + integrate, as csrc/mapc.cu launches it
+            cuda_emu::launch(dim3((n_targets + 255) / 256), dim3(256), 0, [&] {
+                mapc::integrate_kernel(a.in, a.out, a.pos_next, a.partial, n_local, S, i_first, n_targets, dt, damping);
+            });
+            ++launches;
+        }
+        for (unsigned c : counters) counters_clean = counters_clean && c == 0u;
+        counters_clean = counters_clean && done == 0u;
+        if (fuse && !(stamps[0] != 0 && stamps[1] >= stamps[0])) counters_clean = false;
+        std::memcpy(out + i_first, out_local.data(), (size_t)n_local * sizeof(PV));
+        for (int i = 0; i < n_local; ++i) std::memcpy(pos_next_out + 4 * (size_t)(i_first + i), &pos_next[i_first + i], 16);
+    }
+    if (info) {
+        info[0] = launches;
+        info[1] = fence_word;
+        info[2] = counters_clean ? 1 : 0;
+    }
+    return 0;
+}
+
+// The literal CSMain step (well_step_kernel) of one rank's shard [i_first, i_first + n_local): out and
+// pos_next_out as above.  Also runs pack_positions_kernel over `in` into packed_out (n float4).
+int emu_step_well(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next_out, float *packed_out, int n,
+                  int n_active, float dt, float damping, int i_first, int n_local)
+{
+    const int n_targets = local_targets(n, i_first, n_local, n_active);
+    std::vector<PV> in_local(n_local), out_local(n_local);
+    std::memcpy(in_local.data(), in + i_first, (size_t)n_local * sizeof(PV));
+    std::memcpy(out_local.data(), out + i_first, (size_t)n_local * sizeof(PV));
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    std::vector<float4> pos_next(n, make_float4(nan, nan, nan, nan)), packed(n, make_float4(nan, nan, nan, nan));
+    const mapc_posvelo *pin = reinterpret_cast<const mapc_posvelo *>(in_local.data());
+    mapc_posvelo *pout = reinterpret_cast<mapc_posvelo *>(out_local.data());
+    if (n_targets > 0)
+        cuda_emu::launch(dim3((n_targets + 255) / 256), dim3(256), 0, [&] {
+            mapc::well_step_kernel(pin, pout, pos_next.data(), i_first, n_targets, dt, damping);
+        });
+    std::vector<PV> all(n);
+    std::memcpy(all.data(), in, (size_t)n * sizeof(PV));
+    cuda_emu::launch(dim3((n + 255) / 256), dim3(256), 0, [&] {
+        mapc::pack_positions_kernel(reinterpret_cast<const mapc_posvelo *>(all.data()), packed.data(), n);
+    });
+    std::memcpy(out + i_first, out_local.data(), (size_t)n_local * sizeof(PV));
+    std::memcpy(pos_next_out, pos_next.data(), (size_t)n * 16);
+    std::memcpy(packed_out, packed.data(), (size_t)n * 16);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+"""The product's CUDA kernel SOURCE, run on the CPU (no GPU needed) and compared with the oracle bit for bit.
+
+tests/emu/ compiles csrc/nbody_kernels.cuh -- unchanged; its few lines of PTX have host stand-ins -- with g++
+over a shim in which one OS thread plays one CUDA thread and __syncthreads() is a barrier, and drives
+force_cells_kernel / integrate_kernel with the StepArgs, segment lists, launch shapes (csrc/force_shapes.inc)
+and two-launch local/remote split that csrc/mapc.cu uses.  With MUFU.RSQ replaced by the correctly rounded
+1/sqrt, the kernel's arithmetic is exactly the oracle's MIRRORED flavour, so every output bit must agree:
+this pins the kernels' indexing, staging, ragged tails, canonical segment order, arrival counters and the
+fused combine + integrate -- everything except what only the hardware adds (the `-m gpu` tests cover that).
+The emulation is test infrastructure: nothing in the product path includes it.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "emu")
+
+# (pairs per thread, threads per block) of csrc/force_shapes.inc
+SHAPES = [(4, 256), (4, 128), (2, 128), (2, 64), (1, 64), (1, 32)]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    res = subprocess.run(["make", "-C", EMU_DIR], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    lib = ctypes.CDLL(os.path.join(EMU_DIR, "libmapc_emu.so"))
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.emu_step_allpairs.restype = ci
+    lib.emu_step_allpairs.argtypes = [vp, vp, vp, ci, ci, cf, cf, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+    lib.emu_step_well.restype = ci
+    lib.emu_step_well.argtypes = [vp, vp, vp, vp, ci, ci, cf, cf, ci, ci]
+    return lib
+
+
+def emu_step(lib, particles, S, shape, n_active=None, dt=0.1, damping=1.0, fuse=True, mass_in_loop=False,
+             world=1, peer=False, block_order=0, stale=None):
+    """-> (written side, packed mirror, info) after one emulated step."""
+    n = particles.shape[0]
+    n_active = n if n_active is None else n_active
+    inp = np.ascontiguousarray(particles)
+    out = np.ascontiguousarray(stale.copy() if stale is not None else particles.copy())
+    mirror = np.full((n, 4), np.nan, dtype=np.float32)
+    info = np.zeros(3, dtype=np.uint64)
+    rc = lib.emu_step_allpairs(inp.ctypes.data, out.ctypes.data, mirror.ctypes.data, n, n_active, dt, damping, S,
+                               shape[0], shape[1], int(fuse), int(mass_in_loop), world, int(peer), block_order,
+                               info.ctypes.data)
+    assert rc == 0, f"emu_step_allpairs returned {rc}"
+    return out, mirror, info
+
+
+def oracle_step(oracle, particles, S, n_active=None, dt=0.1, damping=1.0, stale=None, flavour=None):
+    out = stale.copy() if stale is not None else particles.copy()
+    return oracle.step_allpairs(particles, n_active=n_active, dt=dt, damping=damping, S=S,
+                                flavour=oracle.MIRRORED if flavour is None else flavour, out=out)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 300, 1000])
+def test_fused_kernel_equals_mirrored_oracle_bitwise(emu, oracle, mapc, shape, n):
+    """Every launch shape, sizes straddling the 64-body tile and the ragged last tile (N = 1000: 15.6 tiles,
+    S = 32 segments of 0 or 1 tile -- empty segments included)."""
+    p = mapc.ic.uniform_sphere(n, 300.0, seed=1000 + n, speed=2.0)
+    S = mapc.plan_segments(n)
+    got, mirror, info = emu_step(emu, p, S, shape, dt=0.05, damping=0.995)
+    ref = oracle_step(oracle, p, S, dt=0.05, damping=0.995)
+    assert got.tobytes() == ref.tobytes()
+    assert mirror.tobytes() == ref["pos"].tobytes()          # the packed mirror the next step's j loop reads
+    assert info[0] == 1 and info[1] == 42 and info[2] == 1   # one launch; fence written; counters re-armed
+
+
+@pytest.mark.parametrize("shape", [(4, 256), (2, 128), (1, 32)])
+def test_longer_segments_and_stage_boundaries(emu, oracle, mapc, shape):
+    """Segments longer than one 256-body stage (S = 2 over 1,100 sources: 9 and 9 tiles -> 576 + 524 bodies,
+    stages of 256/64 with a partial last stage and the ragged last tile), so the prefetch / double-buffer
+    path and the per-stage tile loop run several times."""
+    n = 1100
+    p = mapc.ic.plummer(n, 80.0, seed=5)
+    for S in (1, 2, 3):
+        got, mirror, _ = emu_step(emu, p, S, shape)
+        ref = oracle_step(oracle, p, S)
+        assert got.tobytes() == ref.tobytes(), S
+        assert mirror.tobytes() == ref["pos"].tobytes()
+
+
+def test_unfused_path_and_block_order_do_not_change_bits(emu, oracle, mapc):
+    """MAPC_FUSE=0 (force cells + separate integrate_kernel) and the fused kernel with its blocks run in
+    the opposite order (another block arrives last at every counter) give the same bits."""
+    n = 700
+    p = mapc.ic.uniform_sphere(n, 200.0, seed=3, speed=1.0)
+    S = mapc.plan_segments(n)
+    ref = oracle_step(oracle, p, S)
+    for shape in ((4, 128), (1, 64)):
+        fused, _, _ = emu_step(emu, p, S, shape)
+        reverse, _, info_r = emu_step(emu, p, S, shape, block_order=1)
+        unfused, mirror_u, info_u = emu_step(emu, p, S, shape, fuse=False)
+        assert fused.tobytes() == ref.tobytes()
+        assert reverse.tobytes() == ref.tobytes() and info_r[2] == 1
+        assert unfused.tobytes() == ref.tobytes() and mirror_u.tobytes() == ref["pos"].tobytes()
+        assert info_u[0] == 2                                # force launch + integrate launch
+
+
+@pytest.mark.parametrize("n_active", [1, 64, 100, 640, 999])
+def test_n_active_updates_whole_thread_groups_only(emu, oracle, mapc, n_active):
+    """Simulate(n_active): sources j < n_active, targets = ceil(n_active/64) groups of 64 (Compute.cpp:1041,
+    writes past N dropped); the other bodies of the written side keep their stale contents."""
+    n = 1000
+    p = mapc.ic.uniform_sphere(n, 250.0, seed=8, speed=1.0)
+    stale = p.copy()
+    stale["pos"] += 3.0
+    S = mapc.plan_segments(n_active)
+    got, _, _ = emu_step(emu, p, S, (2, 64), n_active=n_active, stale=stale)
+    ref = oracle_step(oracle, p, S, n_active=n_active, stale=stale)
+    assert got.tobytes() == ref.tobytes()
+    t = oracle.num_targets(n, n_active)
+    assert got[t:].tobytes() == stale[t:].tobytes()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("peer", [False, True])
+def test_sharded_ranks_equal_unsharded_bitwise(emu, oracle, mapc, world, peer):
+    """i-sharding as csrc/mapc.cu lays it out: every rank evaluates the cells of its own targets, local
+    segments in one launch and remote segments in a second one that shares the arrival counters.  With the
+    peer layout each rank's packed array is NaN outside its own shard, so a remote cell that did not go
+    through seg_src[] (indexed like the launch's segment list) would poison the result."""
+    n = 2048                       # 32 tiles, S = 32: one tile per segment, S/world segments per rank
+    p = mapc.ic.uniform_sphere(n, 400.0, seed=11, speed=1.0)
+    S = mapc.plan_segments(n)
+    ref = oracle_step(oracle, p, S)
+    for shape in ((2, 128), (1, 32)):
+        got, mirror, info = emu_step(emu, p, S, shape, world=world, peer=peer)
+        assert got.tobytes() == ref.tobytes(), (shape, world, peer)
+        assert mirror.tobytes() == ref["pos"].tobytes()
+        assert info[0] == 2 * world and info[2] == 1          # local + remote launch per rank
+
+
+def test_mass_in_loop_variant_stays_at_rounding_level(emu, oracle, mapc):
+    """MAPC_MASS_IN_LOOP=1 (the shader's per-pair mass multiply, 12 lane-ops) has no oracle flavour with its
+    exact fma placement; it must sit within rounding of both flavours."""
+    n = 900
+    p = mapc.ic.uniform_sphere(n, 300.0, seed=21, speed=1.0)
+    S = mapc.plan_segments(n)
+    got, _, _ = emu_step(emu, p, S, (4, 128), mass_in_loop=True)
+    for flavour in (oracle.LITERAL, oracle.MIRRORED):
+        err = oracle.rel_errors(got, oracle_step(oracle, p, S, flavour=flavour))
+        assert max(err.values()) < 2e-6, err
+
+
+@pytest.mark.parametrize("n,n_active,shard", [(1000, 1000, (0, 1000)), (1000, 130, (0, 1000)), (1024, 1024, (512, 512))])
+def test_well_and_pack_kernels(emu, oracle, mapc, n, n_active, shard):
+    """well_step_kernel -- the literal CSMain the reference dispatches (nBodyGravityCS.hlsl:86-109) -- and
+    pack_positions_kernel, bit for bit against the oracle's MIRRORED well step; also on the second shard of
+    two, where the kernel indexes PosVelo locally and the packed mirror globally."""
+    p = mapc.ic.uniform_sphere(n, 300.0, seed=31, speed=4.0)
+    stale = p.copy()
+    stale["velo"] += 1.0
+    got = np.ascontiguousarray(stale.copy())
+    mirror = np.empty((n, 4), dtype=np.float32)
+    packed = np.empty((n, 4), dtype=np.float32)
+    first, count = shard
+    rc = emu.emu_step_well(np.ascontiguousarray(p).ctypes.data, got.ctypes.data, mirror.ctypes.data,
+                           packed.ctypes.data, n, n_active, 0.05, 0.995, first, count)
+    assert rc == 0
+    ref = oracle.step_well(p, n_active=n_active, dt=0.05, damping=0.995, flavour=oracle.MIRRORED, out=stale.copy())
+    t = oracle.num_targets(n, n_active)
+    lo, hi = first, min(first + count, t)
+    assert got[lo:hi].tobytes() == ref[lo:hi].tobytes()
+    assert got[hi:first + count].tobytes() == stale[hi:first + count].tobytes()    # not dispatched: untouched
+    assert got[:first].tobytes() == stale[:first].tobytes()                        # another rank's shard
+    assert mirror[lo:hi].tobytes() == ref["pos"][lo:hi].tobytes()
+    assert packed.tobytes() == p["pos"].tobytes()
