@@ -370,6 +370,7 @@ struct Switches {
     bool pdl;           // MAPC_PDL=0: no programmatic dependent launch between consecutive steps
     bool tma;           // MAPC_TMA=1: cp.async.bulk source staging instead of LDG/STS
     bool shfl;          // MAPC_SHFL=1: warp-shuffle broadcast of staged sources instead of LDS broadcast
+    bool chunk;         // MAPC_CHUNK=1 (experimental, changes the bits): chains bounded at kChunkSources sources
     bool mass_in_loop;  // MAPC_MASS_IN_LOOP=1: 12-op pair with the shader's per-pair mass multiply
     bool timers;        // MAPC_TIMERS=0: no "simulate ms" timer at all
     bool timer_events;  // MAPC_TIMER_EVENTS=1: cudaEvent pairs instead of in-kernel stamps
@@ -385,6 +386,7 @@ Switches read_switches()
     w.pdl = env_int("MAPC_PDL", 1) != 0;
     w.tma = env_int("MAPC_TMA", 0) != 0;
     w.shfl = env_int("MAPC_SHFL", 0) != 0;
+    w.chunk = env_int("MAPC_CHUNK", 0) != 0;
     w.mass_in_loop = env_int("MAPC_MASS_IN_LOOP", 0) != 0;
     w.timers = env_int("MAPC_TIMERS", 1) != 0;
     w.timer_events = env_int("MAPC_TIMER_EVENTS", 0) != 0;
@@ -534,10 +536,10 @@ void resolve_timers(mapc_compute *c, bool block)
 
 // grid = (target blocks, segments of this launch): one cell per thread block
 template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER, bool INLOOP, bool TMA,
-          bool SHFL = false>
+          bool SHFL = false, int CHUNK = 0>
 mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream_t stream)
 {
-    auto kernel = mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER, TMA, INLOOP, SHFL>;
+    auto kernel = mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER, TMA, INLOOP, SHFL, CHUNK>;
     dim3 grid((unsigned)args.n_iblocks, (unsigned)args.segs.count, 1);
     if (c->pdl_next) {
         // batched steps: the grid may be scheduled while the previous step's grid drains (the kernel
@@ -567,7 +569,10 @@ mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream
 //                            of the 256-body-stage shapes: a wash, +0.7 % unfused in tools/ubench, -0.8 %
 //                            for the fused kernel (24.29 vs 24.09 ms at N = 262,144);
 //   kStageShfl  MAPC_SHFL=1  warp-shuffle broadcast of the staged bodies instead of the LDS broadcast.
-enum Staging { kStageDefault = 0, kStageTma = 1, kStageShfl = 2 };
+// A third alternative is NOT bit-identical (experimental, never the default):
+//   kStageChunk MAPC_CHUNK=1 chains bounded at kChunkSources sources: chunk sums folded into the partial.
+enum Staging { kStageDefault = 0, kStageTma = 1, kStageShfl = 2, kStageChunk = 3 };
+constexpr int kChunkSources = 2048;
 
 template <bool FUSE, bool PEER = false, bool INLOOP = false>
 mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::StepArgs &args, cudaStream_t stream,
@@ -577,10 +582,14 @@ mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::Step
     constexpr bool kAlt = FUSE && !PEER && !INLOOP;   // the alternatives are instantiated for this path only
     const bool tma = kAlt && staging == kStageTma;
     const bool shfl = kAlt && staging == kStageShfl;
+    if (staging == kStageChunk && !kAlt)
+        return fail(MAPC_ERR_UNSUPPORTED, "MAPC_CHUNK=1 exists for the fused, non-peer, mass-per-partial kernel only");
+    const bool chunk = kAlt && staging == kStageChunk;
 #define MAPC_SHAPE(P, T, TJ, U, MINB, ORDER, HAS_TMA)                                                          \
     if (pl.pairs == P && pl.threads == T) {                                                                   \
         if (HAS_TMA && tma) return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, kAlt && HAS_TMA>(c, args, stream); \
         if (shfl) return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false, kAlt>(c, args, stream); \
+        if (chunk) return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false, false, kAlt ? kChunkSources : 0>(c, args, stream); \
         return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false>(c, args, stream);             \
     }
     // unroll / order / blocks-per-SM per shape from the fused kernel measured in the library at N = 262,144
@@ -1055,7 +1064,7 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             args.fence_value = c->fence_write_next;
             mapc::SegList local{0, {}}, remote{0, {}};
             int owner[MAPC_MAX_SEGMENTS];
-            bool peer = c->peer_mode && fuse && n_sources == (int)c->n && sw.peer && !sw.mass_in_loop;
+            bool peer = c->peer_mode && fuse && n_sources == (int)c->n && sw.peer && !sw.mass_in_loop && !sw.chunk;
             for (int s = 0; s < pl.segments; ++s) {
                 int j0, j1;
                 mapc::segment_range(n_sources, pl.segments, s, j0, j1);
@@ -1079,7 +1088,7 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             // MAPC_MASS_IN_LOOP=1: the shader's per-pair `mass * invDistCube` (12 lane-ops) instead of the
             // default once-per-partial scale (11): A/B switch, fused non-peer path only
             const bool inloop = fuse && sw.mass_in_loop;
-            const Staging staging = sw.shfl ? kStageShfl : (sw.tma ? kStageTma : kStageDefault);
+            const Staging staging = sw.chunk ? kStageChunk : (sw.shfl ? kStageShfl : (sw.tma ? kStageTma : kStageDefault));
             auto launch = [&](cudaStream_t st) -> mapc_status {
                 if (inloop) return launch_force_shape<true, false, true>(c, pl, args, st, staging);
                 return fuse ? launch_force_shape<true>(c, pl, args, st, staging)

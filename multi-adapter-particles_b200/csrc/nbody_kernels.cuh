@@ -265,12 +265,21 @@ __device__ __forceinline__ void fence_mbarrier_init() { asm volatile("fence.mbar
 // uniform-address LDS.128 per source.  Same bodies in the same order, so bit-identical; measured
 // slower (profiles/), because the shared-memory broadcast read is already a single instruction per
 // source and the shuffles triple the non-FMA issue slots.  Off by default (MAPC_SHFL=1).
+// CHUNK > 0 (experimental, MAPC_CHUNK=1, off by default): the canonical order with bounded chains.  A
+// segment's sources are taken in chunks of CHUNK bodies (counted from the segment's first source); each
+// chunk is one sequential fp32 chain as before, and the chunk sums -- scaled by the mass like a partial --
+// are folded left to right into the segment's partial in global memory, ((c0 + c1) + c2) + ...  That
+// bounds the rounding noise of a chain independently of S and N at the price of one
+// 16-byte read-modify-write per target per CHUNK sources.  It changes the bits wherever a segment is
+// longer than CHUNK; the oracle's `chunk` parameter states the same order.
 template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER = false, bool TMA = false,
-          bool MASS_IN_LOOP = false, bool SHFL = false>
+          bool MASS_IN_LOOP = false, bool SHFL = false, int CHUNK = 0>
 __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_constant__ StepArgs a)
 {
     constexpr int kLoads = TJ / T;  // staging loads per thread per stage
     static_assert(TJ % T == 0 && TJ % MAPC_BLOCK_SIZE == 0, "stage must be a multiple of block and tile size");
+    static_assert(CHUNK % TJ == 0, "a chunk is a whole number of stages");
+    constexpr int kStagesPerChunk = CHUNK > 0 ? CHUNK / TJ : 1;
     __shared__ __align__(128) float4 tile[2][TJ];
     __shared__ __align__(8) unsigned long long full_bar[2];
     __shared__ int s_is_last;
@@ -326,6 +335,7 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
         }
 
         const int n_stages = (j1 - j0 + TJ - 1) / TJ;
+        int flushed = 0;  // CHUNK: chunk sums already folded into this cell's partial
         float4 stage[kLoads];
         if (TMA) {
             if (n_stages > 0 && tid == 0) {
@@ -416,6 +426,39 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                 for (int l = 0; l < kLoads; ++l) tile[buf ^ 1][l * T + tid] = stage[l];
             }
             __syncthreads();
+            if (CHUNK > 0 && has_next && (t + 1) % kStagesPerChunk == 0) {
+                // end of a chunk with more sources to come: fold the chain into the partial, start a new one
+                float4 *part = a.partial + (size_t)seg * a.partial_stride;
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const int ia = i_block + (2 * p) * T + tid;
+                    const int ib2 = i_block + (2 * p + 1) * T + tid;
+                    if (!MASS_IN_LOOP) {
+                        const float2 m = make_float2(MAPC_PARTICLE_MASS, MAPC_PARTICLE_MASS);
+                        ax[p] = __fmul2_rn(ax[p], m);
+                        ay[p] = __fmul2_rn(ay[p], m);
+                        az[p] = __fmul2_rn(az[p], m);
+                    }
+                    if (ia < a.i_cnt) {
+                        float4 v = make_float4(ax[p].x, ay[p].x, az[p].x, 0.f);
+                        if (flushed > 0) {
+                            const float4 o = part[ia];
+                            v = make_float4(__fadd_rn(o.x, v.x), __fadd_rn(o.y, v.y), __fadd_rn(o.z, v.z), 0.f);
+                        }
+                        part[ia] = v;
+                    }
+                    if (ib2 < a.i_cnt) {
+                        float4 v = make_float4(ax[p].y, ay[p].y, az[p].y, 0.f);
+                        if (flushed > 0) {
+                            const float4 o = part[ib2];
+                            v = make_float4(__fadd_rn(o.x, v.x), __fadd_rn(o.y, v.y), __fadd_rn(o.z, v.z), 0.f);
+                        }
+                        part[ib2] = v;
+                    }
+                    ax[p] = ay[p] = az[p] = make_float2(0.f, 0.f);
+                }
+                ++flushed;
+            }
         }
 
         float4 *out = a.partial + (size_t)seg * a.partial_stride;
@@ -428,6 +471,17 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                 ax[p] = __fmul2_rn(ax[p], m);
                 ay[p] = __fmul2_rn(ay[p], m);
                 az[p] = __fmul2_rn(az[p], m);
+            }
+            if (CHUNK > 0 && flushed > 0) {  // the last chunk joins the earlier ones
+                if (ia < a.i_cnt) {
+                    const float4 o = out[ia];
+                    out[ia] = make_float4(__fadd_rn(o.x, ax[p].x), __fadd_rn(o.y, ay[p].x), __fadd_rn(o.z, az[p].x), 0.f);
+                }
+                if (ib2 < a.i_cnt) {
+                    const float4 o = out[ib2];
+                    out[ib2] = make_float4(__fadd_rn(o.x, ax[p].y), __fadd_rn(o.y, ay[p].y), __fadd_rn(o.z, az[p].y), 0.f);
+                }
+                continue;
             }
             if (ia < a.i_cnt) out[ia] = make_float4(ax[p].x, ay[p].x, az[p].x, 0.f);
             if (ib2 < a.i_cnt) out[ib2] = make_float4(ax[p].y, ay[p].y, az[p].y, 0.f);

@@ -185,6 +185,17 @@ static void segment_block_mirrored(const mapo_posvelo *in, int j0, int j1,
 void mapo_accel_allpairs(const mapo_posvelo *in, int n_sources, int S, int flavour,
                          const int *targets, int n_targets, float *accel3, int threads)
 {
+    mapo_accel_allpairs_chunked(in, n_sources, S, 0, flavour, targets, n_targets, accel3, threads);
+}
+
+/* chunk > 0: the canonical order with bounded chains (csrc/nbody_kernels.cuh, template flag CHUNK): a
+ * segment longer than `chunk` sources is evaluated as consecutive chunks of `chunk` sources counted from
+ * the segment's first source; every chunk is one sequential chain (scaled by the mass like a partial in
+ * the MIRRORED flavour) and the chunk sums are folded left to right, ((c0 + c1) + c2) + ..., into the
+ * segment's partial.  chunk == 0: one chain per segment. */
+void mapo_accel_allpairs_chunked(const mapo_posvelo *in, int n_sources, int S, int chunk, int flavour,
+                                 const int *targets, int n_targets, float *accel3, int threads)
+{
     const int blocks = (n_targets + LANES - 1) / LANES;
     if (threads <= 0) threads = mapo_max_threads();
 #pragma omp parallel for schedule(dynamic, 4) num_threads(threads)
@@ -203,12 +214,23 @@ void mapo_accel_allpairs(const mapo_posvelo *in, int n_sources, int S, int flavo
         }
         for (int s = 0; s < S; ++s) {
             int j0, j1;
-            float px[LANES], py[LANES], pz[LANES];
+            float px[LANES] = {0.f}, py[LANES] = {0.f}, pz[LANES] = {0.f};
             mapo_segment_range(n_sources, S, s, &j0, &j1);
-            if (flavour == MAPO_LITERAL)
-                segment_block_literal(in, j0, j1, xi, yi, zi, px, py, pz);
-            else
-                segment_block_mirrored(in, j0, j1, xi, yi, zi, px, py, pz);
+            const int step = (chunk > 0 && j1 - j0 > chunk) ? chunk : (j1 - j0 > 0 ? j1 - j0 : 1);
+            int c0 = j0;
+            do {                                              /* one pass unless the segment is chunked */
+                const int c1 = (c0 + step < j1) ? c0 + step : j1;
+                float cx[LANES], cy[LANES], cz[LANES];
+                if (flavour == MAPO_LITERAL)
+                    segment_block_literal(in, c0, c1, xi, yi, zi, cx, cy, cz);
+                else
+                    segment_block_mirrored(in, c0, c1, xi, yi, zi, cx, cy, cz);
+                for (int l = 0; l < LANES; ++l) {
+                    if (c0 == j0) { px[l] = cx[l]; py[l] = cy[l]; pz[l] = cz[l]; }
+                    else { px[l] += cx[l]; py[l] += cy[l]; pz[l] += cz[l]; }
+                }
+                c0 = c1;
+            } while (c0 < j1);
             for (int l = 0; l < LANES; ++l) { tx[l] += px[l]; ty[l] += py[l]; tz[l] += pz[l]; }
         }
         for (int l = 0; l < LANES; ++l) {
@@ -280,13 +302,21 @@ void mapo_step_allpairs_targets(const mapo_posvelo *in, int n_sources,
                                 const int *targets, int n_targets, float dt, float damping,
                                 int S, int flavour, int threads, mapo_posvelo *out_targets)
 {
+    mapo_step_allpairs_targets_chunked(in, n_sources, targets, n_targets, dt, damping, S, 0, flavour, threads,
+                                       out_targets);
+}
+
+void mapo_step_allpairs_targets_chunked(const mapo_posvelo *in, int n_sources,
+                                        const int *targets, int n_targets, float dt, float damping,
+                                        int S, int chunk, int flavour, int threads, mapo_posvelo *out_targets)
+{
     enum { CHUNK = 4096 };
     float buf[3 * CHUNK];
     int ids[CHUNK];
     for (int base = 0; base < n_targets; base += CHUNK) {
         const int cnt = (n_targets - base) < CHUNK ? (n_targets - base) : CHUNK;
         for (int q = 0; q < cnt; ++q) ids[q] = targets ? targets[base + q] : base + q;
-        mapo_accel_allpairs(in, n_sources, S, flavour, ids, cnt, buf, threads);
+        mapo_accel_allpairs_chunked(in, n_sources, S, chunk, flavour, ids, cnt, buf, threads);
         for (int q = 0; q < cnt; ++q)
             mapo_integrate(&in[ids[q]], &buf[3 * q], dt, damping, flavour, &out_targets[base + q]);
     }

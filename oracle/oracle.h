@@ -76,6 +76,11 @@ void mapo_accel_allpairs_scalar(const mapo_posvelo *in, int n_sources, int S, in
  * OpenMP over target blocks; threads <= 0 means omp_get_max_threads(). */
 void mapo_accel_allpairs(const mapo_posvelo *in, int n_sources, int S, int flavour,
                          const int *targets, int n_targets, float *accel3, int threads);
+/* the same with chains bounded at `chunk` sources (0 = one chain per segment): a longer segment is taken as
+ * consecutive chunks counted from its first source, each one sequential chain, folded left to right into
+ * the segment's partial -- the order of the kernels' experimental CHUNK variant (MAPC_CHUNK=1) */
+void mapo_accel_allpairs_chunked(const mapo_posvelo *in, int n_sources, int S, int chunk, int flavour,
+                                 const int *targets, int n_targets, float *accel3, int threads);
 /* fp64 direct sum, ascending j, no segments -- reported alongside, never gating */
 void mapo_accel_fp64(const mapo_posvelo *in, int n_sources,
                      const int *targets, int n_targets, double *accel3, int threads);
@@ -92,6 +97,9 @@ void mapo_step_allpairs(const mapo_posvelo *in, mapo_posvelo *out, int n, int n_
 void mapo_step_allpairs_targets(const mapo_posvelo *in, int n_sources,
                                 const int *targets, int n_targets, float dt, float damping,
                                 int S, int flavour, int threads, mapo_posvelo *out_targets);
+void mapo_step_allpairs_targets_chunked(const mapo_posvelo *in, int n_sources,
+                                        const int *targets, int n_targets, float dt, float damping,
+                                        int S, int chunk, int flavour, int threads, mapo_posvelo *out_targets);
 /* the step the reference actually executes: origin gravity well, nBodyGravityCS.hlsl:86-109 */
 void mapo_step_well(const mapo_posvelo *in, mapo_posvelo *out, int n, int n_active,
                     float dt, float damping, int flavour);

@@ -56,6 +56,11 @@ def load() -> ctypes.CDLL:
     lib.mapo_accel_allpairs_scalar.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
     lib.mapo_accel_allpairs.restype = None
     lib.mapo_accel_allpairs.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int]
+    lib.mapo_accel_allpairs_chunked.restype = None
+    lib.mapo_accel_allpairs_chunked.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int]
+    lib.mapo_step_allpairs_targets_chunked.restype = None
+    lib.mapo_step_allpairs_targets_chunked.argtypes = [c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_int,
+                                                       c_int, c_int, c_int, c_void_p]
     lib.mapo_accel_fp64.restype = None
     lib.mapo_accel_fp64.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int]
     lib.mapo_integrate.restype = None
@@ -122,7 +127,7 @@ def body_body_interaction(ai, bj, bi, mass=70000.0, particles=1, flavour=LITERAL
 
 
 def accel_allpairs(particles, n_sources=None, S=None, flavour=LITERAL, targets=None, threads=0,
-                   scalar=False) -> np.ndarray:
+                   scalar=False, chunk=0) -> np.ndarray:
     p = _pv(particles)
     n_sources = p.shape[0] if n_sources is None else n_sources
     S = default_segments(n_sources) if S is None else S
@@ -133,7 +138,10 @@ def accel_allpairs(particles, n_sources=None, S=None, flavour=LITERAL, targets=N
         nt, tp = t.shape[0], _ptr(t)
     out = np.zeros((nt, 3), dtype=np.float32)
     if scalar:
+        assert chunk == 0
         load().mapo_accel_allpairs_scalar(_ptr(p), n_sources, S, flavour, tp, nt, _ptr(out))
+    elif chunk:
+        load().mapo_accel_allpairs_chunked(_ptr(p), n_sources, S, chunk, flavour, tp, nt, _ptr(out), threads)
     else:
         load().mapo_accel_allpairs(_ptr(p), n_sources, S, flavour, tp, nt, _ptr(out), threads)
     return out
@@ -153,24 +161,36 @@ def accel_fp64(particles, n_sources=None, targets=None, threads=0) -> np.ndarray
 
 
 def step_allpairs(particles, n_active=None, dt=0.1, damping=1.0, S=None, flavour=LITERAL, threads=0,
-                  out=None) -> np.ndarray:
-    """One all-pairs step.  `out` (the side being overwritten) defaults to a copy of the input."""
+                  out=None, chunk=0) -> np.ndarray:
+    """One all-pairs step.  `out` (the side being overwritten) defaults to a copy of the input.
+    chunk > 0: chains bounded at `chunk` sources (the kernels' experimental CHUNK order)."""
     p = _pv(particles)
     n = p.shape[0]
     n_active = n if n_active is None else n_active
     S = default_segments(min(n_active, n)) if S is None else S
     o = p.copy() if out is None else out
+    if chunk:
+        nt = num_targets(n, n_active)
+        new = np.zeros(nt, dtype=POSVELO_DTYPE)
+        load().mapo_step_allpairs_targets_chunked(_ptr(p), min(n_active, n), None, nt, dt, damping, S, chunk,
+                                                  flavour, threads, _ptr(new))
+        o[:nt] = new
+        return o
     load().mapo_step_allpairs(_ptr(p), _ptr(o), n, n_active, dt, damping, S, flavour, threads)
     return o
 
 
 def step_allpairs_targets(particles, targets, n_sources=None, dt=0.1, damping=1.0, S=None, flavour=LITERAL,
-                          threads=0) -> np.ndarray:
+                          threads=0, chunk=0) -> np.ndarray:
     p = _pv(particles)
     n_sources = p.shape[0] if n_sources is None else n_sources
     S = default_segments(n_sources) if S is None else S
     t = np.ascontiguousarray(targets, dtype=np.int32)
     o = np.zeros(t.shape[0], dtype=POSVELO_DTYPE)
+    if chunk:
+        load().mapo_step_allpairs_targets_chunked(_ptr(p), n_sources, _ptr(t), t.shape[0], dt, damping, S, chunk,
+                                                  flavour, threads, _ptr(o))
+        return o
     load().mapo_step_allpairs_targets(_ptr(p), n_sources, _ptr(t), t.shape[0], dt, damping, S, flavour,
                                       threads, _ptr(o))
     return o

@@ -27,24 +27,31 @@ namespace {
 using mapc::StepArgs;
 
 template <int P, int T, int TJ, int U, int MINB, int ORDER>
-void launch_shape(bool fuse, bool peer, bool inloop, const StepArgs &a, int order)
+bool launch_shape(bool fuse, bool peer, bool inloop, int chunk, const StepArgs &a, int order)
 {
     const dim3 grid((unsigned)a.n_iblocks, (unsigned)a.segs.count, 1), block(T, 1, 1);
-    if (a.segs.count == 0 || a.i_cnt <= 0) return;
+    if (a.segs.count == 0 || a.i_cnt <= 0) return true;
+    if (chunk != 0) {
+        // MAPC_CHUNK=1: csrc/mapc.cu has it for the fused, non-peer, mass-per-partial kernel only, with
+        // 2,048-source chunks; 256 is instantiated here as well so that small problems have several chunks
+        if (!fuse || peer || inloop) return false;
+        if (chunk == 2048) cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, false, false, false, false, 2048>(a); });
+        else if (chunk == 256) cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, false, false, false, false, 256>(a); });
+        else return false;
+        return true;
+    }
     // the instantiations csrc/mapc.cu launches (TMA and SHFL staging are hardware A/Bs, not emulated)
     if (fuse && peer) cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, true>(a); });
     else if (fuse && inloop) cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, false, false, true>(a); });
     else if (fuse) cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, false>(a); });
     else cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, false, false>(a); });
+    return true;
 }
 
-bool launch_force(int pairs, int threads, bool fuse, bool peer, bool inloop, const StepArgs &a, int order)
+bool launch_force(int pairs, int threads, bool fuse, bool peer, bool inloop, int chunk, const StepArgs &a, int order)
 {
-#define MAPC_SHAPE(P, T, TJ, U, MINB, ORDER, HAS_TMA)                 \
-    if (pairs == P && threads == T) {                                 \
-        launch_shape<P, T, TJ, U, MINB, ORDER>(fuse, peer, inloop, a, order); \
-        return true;                                                  \
-    }
+#define MAPC_SHAPE(P, T, TJ, U, MINB, ORDER, HAS_TMA) \
+    if (pairs == P && threads == T) return launch_shape<P, T, TJ, U, MINB, ORDER>(fuse, peer, inloop, chunk, a, order);
 #include "../../multi-adapter-particles_b200/csrc/force_shapes.inc"
 #undef MAPC_SHAPE
     return false;
@@ -73,10 +80,12 @@ extern "C" {
 // that are not targets keep them).  pos_next_out: n float4, the packed mirror of the written side as rank 0
 // .. world-1 wrote it (own shards only).  info[0] = kernel launches, info[1] = fence word after the step,
 // info[2] = 1 if every arrival counter and the `done` counter were back at zero.
-// returns 0, or -1 for an unknown shape, -2 for a layout the library would refuse (peer with straddling segments)
+// chunk: 0, or the CHUNK template value (sources per bounded chain: 256 or 2048).
+// returns 0, or -1 for an unknown shape / variant, -2 for a layout the library would refuse (peer with
+// straddling segments)
 int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next_out, int n, int n_active,
                       float dt, float damping, int S, int pairs, int threads, int fuse, int mass_in_loop,
-                      int world, int peer, int block_order, unsigned long long *info)
+                      int world, int peer, int block_order, int chunk, unsigned long long *info)
 {
     if (n % world) return -2;
     const int n_local = n / world;
@@ -132,7 +141,7 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
 
         mapc::SegList local{0, {}}, remote{0, {}};
         int owner[MAPC_MAX_SEGMENTS];
-        bool peer_ok = peer && fuse && n_sources == n && !mass_in_loop;
+        bool peer_ok = peer && fuse && n_sources == n && !mass_in_loop && chunk == 0;
         for (int s = 0; s < S; ++s) {
             int j0, j1;
             mapc::segment_range(n_sources, S, s, j0, j1);
@@ -145,7 +154,7 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
         if (peer && world > 1 && !peer_ok && remote.count > 0) return -2;
 
         a.segs = local;
-        if (!launch_force(pairs, threads, fuse, false, mass_in_loop, a, block_order)) return -1;
+        if (!launch_force(pairs, threads, fuse, false, mass_in_loop, chunk, a, block_order)) return -1;
         launches += (local.count > 0);
         if (local.count > 0) a.stamp_begin = nullptr;
         if (remote.count > 0) {
@@ -158,7 +167,7 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
                 }
                 a.flag_expect = 7;
             }
-            if (!launch_force(pairs, threads, fuse, use_peer, mass_in_loop, a, block_order)) return -1;
+            if (!launch_force(pairs, threads, fuse, use_peer, mass_in_loop, chunk, a, block_order)) return -1;
             ++launches;
         }
         if (!fuse) {

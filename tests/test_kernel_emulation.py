@@ -30,14 +30,14 @@ def emu():
     lib = ctypes.CDLL(os.path.join(EMU_DIR, "libmapc_emu.so"))
     vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     lib.emu_step_allpairs.restype = ci
-    lib.emu_step_allpairs.argtypes = [vp, vp, vp, ci, ci, cf, cf, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+    lib.emu_step_allpairs.argtypes = [vp, vp, vp, ci, ci, cf, cf, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
     lib.emu_step_well.restype = ci
     lib.emu_step_well.argtypes = [vp, vp, vp, vp, ci, ci, cf, cf, ci, ci]
     return lib
 
 
 def emu_step(lib, particles, S, shape, n_active=None, dt=0.1, damping=1.0, fuse=True, mass_in_loop=False,
-             world=1, peer=False, block_order=0, stale=None):
+             world=1, peer=False, block_order=0, stale=None, chunk=0):
     """-> (written side, packed mirror, info) after one emulated step."""
     n = particles.shape[0]
     n_active = n if n_active is None else n_active
@@ -47,15 +47,15 @@ def emu_step(lib, particles, S, shape, n_active=None, dt=0.1, damping=1.0, fuse=
     info = np.zeros(3, dtype=np.uint64)
     rc = lib.emu_step_allpairs(inp.ctypes.data, out.ctypes.data, mirror.ctypes.data, n, n_active, dt, damping, S,
                                shape[0], shape[1], int(fuse), int(mass_in_loop), world, int(peer), block_order,
-                               info.ctypes.data)
+                               chunk, info.ctypes.data)
     assert rc == 0, f"emu_step_allpairs returned {rc}"
     return out, mirror, info
 
 
-def oracle_step(oracle, particles, S, n_active=None, dt=0.1, damping=1.0, stale=None, flavour=None):
+def oracle_step(oracle, particles, S, n_active=None, dt=0.1, damping=1.0, stale=None, flavour=None, chunk=0):
     out = stale.copy() if stale is not None else particles.copy()
     return oracle.step_allpairs(particles, n_active=n_active, dt=dt, damping=damping, S=S,
-                                flavour=oracle.MIRRORED if flavour is None else flavour, out=out)
+                                flavour=oracle.MIRRORED if flavour is None else flavour, out=out, chunk=chunk)
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -172,3 +172,57 @@ def test_well_and_pack_kernels(emu, oracle, mapc, n, n_active, shard):
     assert got[:first].tobytes() == stale[:first].tobytes()                        # another rank's shard
     assert mirror[lo:hi].tobytes() == ref["pos"][lo:hi].tobytes()
     assert packed.tobytes() == p["pos"].tobytes()
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_chunked_order_equals_chunked_oracle_bitwise(emu, oracle, mapc, shape):
+    """The experimental bounded-chain order (kernel template flag CHUNK, MAPC_CHUNK=1; oracle `chunk`): chunk
+    sums folded left to right into the segment partial.  N = 1,100 with 256-source chunks: S = 1 gives one
+    segment of 4 full chunks + a ragged one, S = 2 segments of 576 and 524 (2 chunks + remainder), S = 32
+    segments shorter than a chunk (then nothing changes and the result equals the unchunked order)."""
+    n = 1100
+    p = mapc.ic.plummer(n, 80.0, seed=5)
+    for S in (1, 2, 32):
+        got, mirror, info = emu_step(emu, p, S, shape, chunk=256)
+        ref = oracle_step(oracle, p, S, chunk=256)
+        assert got.tobytes() == ref.tobytes(), S
+        assert mirror.tobytes() == ref["pos"].tobytes() and info[2] == 1
+        plain = oracle_step(oracle, p, S)
+        assert (got.tobytes() == plain.tobytes()) == (S == 32)
+    # a segment that is an exact multiple of the chunk: the last chunk is folded by the final store
+    q = mapc.ic.uniform_sphere(1024, 200.0, seed=6, speed=1.0)
+    got, _, _ = emu_step(emu, q, 2, shape, chunk=256)
+    assert got.tobytes() == oracle_step(oracle, q, 2, chunk=256).tobytes()
+
+
+def test_chunked_order_product_chunk_size_and_shards(emu, oracle, mapc):
+    """The chunk size the library uses (2,048 sources), on segments of 2,560 sources (N = 5,120, S = 2), and
+    the same through two emulated ranks (local + remote launches fold into the same partials)."""
+    n = 5120
+    p = mapc.ic.uniform_sphere(n, 600.0, seed=13, speed=1.0)
+    ref = oracle_step(oracle, p, 2, chunk=2048)
+    assert ref.tobytes() != oracle_step(oracle, p, 2).tobytes()
+    got, _, _ = emu_step(emu, p, 2, (4, 256), chunk=2048)
+    assert got.tobytes() == ref.tobytes()
+    got2, mirror2, info2 = emu_step(emu, p, 2, (2, 128), chunk=2048, world=2)
+    assert got2.tobytes() == ref.tobytes() and mirror2.tobytes() == ref["pos"].tobytes() and info2[2] == 1
+
+
+def test_bounded_chains_cut_the_rounding_noise(oracle, mapc):
+    """What the chunked order is for: with one chain per segment the noise of the
+    close-pair targets grows with the segment length, with 2,048-source chunks it does not.  N = 262,144,
+    S = 8 (32,768-source segments, the rule the round started with): 1.07e-5 between the CPU flavours without
+    chunks, a few 1e-6 with them."""
+    from scipy.spatial import cKDTree
+    p = mapc.ic.workload("sphere_262144")
+    xyz = p["pos"][:, :3].astype(np.float64)
+    dist, _ = cKDTree(xyz).query(xyz, k=2)
+    close = np.sort(np.argsort(dist[:, 1])[:512]).astype(np.int32)
+
+    def envelope(chunk):
+        lit = oracle.step_allpairs_targets(p, close, S=8, flavour=oracle.LITERAL, chunk=chunk)
+        mir = oracle.step_allpairs_targets(p, close, S=8, flavour=oracle.MIRRORED, chunk=chunk)
+        return max(oracle.rel_errors(mir, lit).values())
+
+    plain, chunked = envelope(0), envelope(2048)
+    assert plain > 8e-6 and chunked < 0.4 * plain, (plain, chunked)
