@@ -1,0 +1,38 @@
+// tests/emu/emu_asan_main.cpp -- TEST INFRASTRUCTURE ONLY: drives the emulated kernels (emu_kernels.cpp) over
+// every launch shape x {fused, unfused, mass-in-loop, chunk 256, chunk 2048, 4 ranks with the peer layout} on
+// exactly-sized heap buffers, for an AddressSanitizer + UBSan build (`make -C tests/emu asan`): any read or
+// write of the kernel source outside its buffers, and any signed overflow / misaligned access, aborts.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cmath>
+struct PV { float pos[4]; float velo[4]; };
+extern "C" int emu_step_allpairs(const void *in, void *out, float *pos_next_out, int n, int n_active,
+                      float dt, float damping, int S, int pairs, int threads, int fuse, int mass_in_loop,
+                      int world, int peer, int block_order, int chunk, unsigned long long *info);
+extern "C" int emu_step_well(const void *in, void *out, float *pos_next_out, float *packed_out, int n,
+                  int n_active, float dt, float damping, int i_first, int n_local);
+int main() {
+    const int shapes[6][2] = {{4,256},{4,128},{2,128},{2,64},{1,64},{1,32}};
+    int runs = 0;
+    for (int n : {1, 65, 1000, 1100, 2048}) {
+        std::vector<PV> in(n), out(n); std::vector<float> mirror(4*n), packed(4*n);
+        srand(n);
+        for (auto &b : in) { for (int k=0;k<3;++k){ b.pos[k] = (rand()%20000)/50.f-200.f; b.velo[k]=(rand()%100)/50.f; } b.pos[3]=0; b.velo[3]=0; }
+        out = in;
+        unsigned long long info[3];
+        for (auto &sh : shapes)
+            for (int S : {1, 2, 32})
+                for (int variant = 0; variant < 6; ++variant) {
+                    int fuse = variant != 1, inloop = variant == 2, chunk = variant == 3 ? 256 : (variant == 4 ? 2048 : 0);
+                    int world = (variant == 5 && n == 2048 && S == 32) ? 4 : 1, peer = world > 1;
+                    int rc = emu_step_allpairs(in.data(), out.data(), mirror.data(), n, n, 0.1f, 1.f, S, sh[0], sh[1], fuse, inloop, world, peer, variant & 1, chunk, info);
+                    if (rc != 0) { printf("rc %d n %d S %d variant %d\n", rc, n, S, variant); return 1; }
+                    ++runs;
+                }
+        emu_step_well(in.data(), out.data(), mirror.data(), packed.data(), n, n, 0.1f, 1.f, 0, n);
+    }
+    printf("asan emulation runs: %d ok\n", runs);
+    return 0;
+}
