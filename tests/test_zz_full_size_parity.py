@@ -50,3 +50,26 @@ def test_full_size_262144_ten_steps_all_targets_lattice(mapc, oracle, gpu):
     err = oracle.rel_errors(got, ref)
     print("N=262,144 lattice, all targets, 10 steps:", err)
     assert max(err.values()) <= TOL_10, err
+
+
+@pytest.mark.xfail(strict=False, reason="experimental opt-in variant (MAPC_CHUNK=1): verified against the oracle by "
+                   "CPU emulation only so far; informational until its first run on hardware")
+def test_experimental_bounded_chain_order(mapc, oracle, gpu):
+    """MAPC_CHUNK=1: chains bounded at 2,048 sources.  N = 131,072 with S = 32 gives
+    segments of 4,096 sources = two chunks each, so the order really differs from the default; the result must
+    match the oracle's `chunk=2048` order like the default matches the plain one."""
+    import os
+    n = 131_072
+    p = mapc.ic.uniform_sphere(n, 6350.0, seed=5)
+    default = gpu_steps(mapc, p, 1)
+    try:
+        os.environ["MAPC_CHUNK"] = "1"
+        chunked = gpu_steps(mapc, p, 1)
+    finally:
+        os.environ.pop("MAPC_CHUNK", None)
+    assert chunked.tobytes() != default.tobytes()
+    lit = oracle.step_allpairs(p, flavour=oracle.LITERAL, chunk=2048)
+    mir = oracle.step_allpairs(p, flavour=oracle.MIRRORED, chunk=2048)
+    err_l, err_m = oracle.rel_errors(chunked, lit), oracle.rel_errors(chunked, mir)
+    print("MAPC_CHUNK=1 vs chunked oracle: literal", err_l, "mirrored", err_m)
+    assert max(err_l.values()) <= TOL_1 and max(err_m.values()) <= 3e-6, (err_l, err_m)

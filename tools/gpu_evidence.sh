@@ -8,6 +8,7 @@
 #   <tag>_bench_n262144.json        bench.py default line (config 3)
 #   <tag>_bench_reference.json      bench.py --impl reference
 #   <tag>_bench_n10000*.json        config 2, single calls and batches of 50
+#   <tag>_bench_*_chunk.json        the same lines with MAPC_CHUNK=1 (bounded chains)
 #   <tag>_launches.csv              ncu launch list of the bench command (gpu__time_duration.sum per launch)
 #   <tag>_force_full.ncu-rep/.csv   ncu --set full of one force kernel launch + its raw page as CSV
 #   <tag>_ncu_traffic.json          dram bytes per launch of that capture, in the format bench.py reads
@@ -34,6 +35,14 @@ timeout 300 python bench.py --bodies 10000 --steps 1000 --warmup 50 --no-l2-flus
     > "$OUT/${TAG}_bench_n10000.json" 2>> "$OUT/${TAG}_bench_n262144.err"
 timeout 300 python bench.py --bodies 10000 --steps 1000 --warmup 50 --batch 50 --no-cpu-baseline \
     > "$OUT/${TAG}_bench_n10000_batched.json" 2>> "$OUT/${TAG}_bench_n262144.err"
+
+step "A/B: bounded-chain order (MAPC_CHUNK=1, experimental) at config 3 and at N = 4,194,304"
+MAPC_CHUNK=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline \
+    > "$OUT/${TAG}_bench_n262144_chunk.json" 2>> "$OUT/${TAG}_bench_n262144.err"
+timeout 600 python bench.py --bodies 4194304 --steps 2 --warmup 3 --no-cpu-baseline \
+    > "$OUT/${TAG}_bench_n4194304.json" 2>> "$OUT/${TAG}_bench_n262144.err"
+MAPC_CHUNK=1 timeout 600 python bench.py --bodies 4194304 --steps 2 --warmup 3 --no-cpu-baseline \
+    > "$OUT/${TAG}_bench_n4194304_chunk.json" 2>> "$OUT/${TAG}_bench_n262144.err"
 
 step "ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
