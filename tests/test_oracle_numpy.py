@@ -75,3 +75,34 @@ def test_well_step_bitwise_equals_numpy_transcription(oracle, mapc):
         new_pos, new_vel = integrate(pos, vel, accel, 0.1, 1.0)
         assert got["pos"][i].tobytes() == new_pos.tobytes(), i
         assert got["velo"][i, :3].tobytes() == new_vel.tobytes(), i
+
+
+def accel_segments_chunked(pos, i, S, chunk, segment_range):
+    """The bounded-chain order (oracle `chunk`, kernel flag CHUNK): a segment longer than `chunk` sources is
+    taken in consecutive chunks counted from its first source, each one sequential chain; the chunk sums are
+    folded left to right into the segment's partial, the partials left to right into the total."""
+    total = np.zeros(3, dtype=F)
+    n = pos.shape[0]
+    for seg in range(S):
+        j0, j1 = segment_range(n, S, seg)
+        step = chunk if (j1 - j0) > chunk else max(j1 - j0, 1)
+        partial = None
+        for c0 in range(j0, max(j1, j0 + 1), step):
+            c = np.zeros(3, dtype=F)
+            for j in range(c0, min(c0 + step, j1)):
+                c = body_body_interaction(c, pos[j], pos[i], PARTICLE_MASS, 1)
+            partial = c if partial is None else (partial + c).astype(F)
+        total = (total + partial).astype(F)
+    return total
+
+
+@pytest.mark.parametrize("n,S,chunk", [(200, 2, 64), (257, 1, 64), (130, 32, 64)])
+def test_chunked_order_bitwise_equals_numpy_transcription(oracle, mapc, n, S, chunk):
+    p = mapc.ic.uniform_sphere(n, 120.0, seed=n, speed=4.0)
+    got = oracle.step_allpairs(p, dt=0.1, damping=0.97, S=S, flavour=oracle.LITERAL, chunk=chunk)
+    pos, vel = p["pos"].astype(F), p["velo"][:, :3].astype(F)
+    for i in range(0, n, 3):
+        a = accel_segments_chunked(pos, i, S, chunk, oracle.segment_range)
+        new_pos, new_vel = integrate(pos[i], vel[i], a, 0.1, 0.97)
+        assert got["pos"][i].tobytes() == new_pos.tobytes(), i
+        assert got["velo"][i, :3].tobytes() == new_vel.tobytes(), i
