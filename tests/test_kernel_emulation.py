@@ -226,3 +226,49 @@ def test_bounded_chains_cut_the_rounding_noise(oracle, mapc):
 
     plain, chunked = envelope(0), envelope(2048)
     assert plain > 8e-6 and chunked < 0.4 * plain, (plain, chunked)
+
+
+GOLDEN = os.path.join(HERE, "golden")
+
+
+def test_emulated_kernels_against_reference_shader_vectors(emu, oracle, mapc):
+    """The chain reference shader -> committed vectors -> kernel source, closed on the CPU: the emulated
+    force kernel against outputs of the reference's own nBodyGravityCS.hlsl code compiled for the CPU
+    (tests/golden/ref_shader_vectors.npz: all-pairs through its bodyBodyInteraction, and the shipped CSMain),
+    at the tolerances the GPU tests use (the kernel's fma placement and mass-per-partial differ from the
+    shader's literal order at rounding level; MUFU.RSQ is the GPU tests' business)."""
+    g = np.load(os.path.join(GOLDEN, "ref_shader_vectors.npz"))
+    for case, dt, damping in (("a", 0.1, 1.0), ("b", 0.05, 0.995)):
+        inp = g[f"allpairs_{case}_in"].view(mapc.POSVELO_DTYPE).reshape(-1)
+        S = int(g[f"allpairs_{case}_S"])
+        assert S == mapc.plan_segments(inp.shape[0])
+        got, _, _ = emu_step(emu, inp, S, (2, 128), dt=dt, damping=damping)
+        err = oracle.rel_errors(got, g[f"allpairs_{case}_out"])
+        assert max(err.values()) <= 1e-5, (case, err)
+    w = np.ascontiguousarray(g["well_in"].view(mapc.POSVELO_DTYPE).reshape(-1))
+    n = w.shape[0]
+    for ref_key, dt, damping in (("well_out_a", 0.1, 1.0), ("well_out_b", 0.05, 0.995)):
+        got = w.copy()
+        mirror = np.empty((n, 4), dtype=np.float32)
+        packed = np.empty((n, 4), dtype=np.float32)
+        assert emu.emu_step_well(w.ctypes.data, got.ctypes.data, mirror.ctypes.data, packed.ctypes.data, n, n,
+                                 dt, damping, 0, n) == 0
+        err = oracle.rel_errors(got, g[ref_key])
+        assert max(err.values()) <= 2e-6, (ref_key, err)
+
+
+@pytest.mark.parametrize("name", ["lattice_1000", "plummer_777"])
+def test_emulated_kernel_trajectory_against_golden(emu, oracle, mapc, name):
+    """Ten ping-pong steps of the emulated fused kernel against the committed LITERAL trajectory (1e-5 after
+    one step, 1e-4 after the last), and bit for bit against the MIRRORED oracle stepped alongside."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    state = g["input"].view(mapc.POSVELO_DTYPE).reshape(-1)
+    dt, damping, steps, S = float(g["dt"]), float(g["damping"]), int(g["steps"]), int(g["S"])
+    mirrored = state
+    for step in range(1, steps + 1):
+        state, _, _ = emu_step(emu, state, S, (1, 64) if step % 2 else (4, 128), dt=dt, damping=damping)
+        mirrored = oracle.step_allpairs(mirrored, dt=dt, damping=damping, S=S, flavour=oracle.MIRRORED)
+        assert state.tobytes() == mirrored.tobytes(), step
+        if step == 1:
+            assert max(oracle.rel_errors(state, g["literal_1"]).values()) <= 1e-5
+    assert max(oracle.rel_errors(state, g["literal_last"]).values()) <= 1e-4
