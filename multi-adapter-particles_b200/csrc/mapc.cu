@@ -25,6 +25,7 @@
 #include "../../include/mapc.h"
 #include "fence.hpp"
 #include "nbody_kernels.cuh"
+#include "step_layout.hpp"
 
 namespace {
 
@@ -349,12 +350,7 @@ static mapc_status require_ungated(const GatedStream *gs, const char *what)
 // ---- launch plan ------------------------------------------------------------------------------
 namespace {
 
-struct Plan {
-    int pairs;    // P: register pairs per thread (2P targets per thread)
-    int threads;  // T
-    int blocks_x; // target blocks of T*2P bodies
-    int segments; // canonical S
-};
+using mapc::Plan;
 
 int env_int(const char *name, int dflt)
 {
@@ -397,38 +393,12 @@ Switches read_switches()
     return w;
 }
 
-// Launch shapes (P, T) with the FMA-pipe efficiency each reaches at large N (tools/ubench,
-// profiles/): all sit on the same 67-72 % plateau, so at large N the choice barely matters, while
-// at small N what decides is how evenly the cells fall on the 4 x SMs warp schedulers and how many
-// target lanes the last block leaves idle.  The shape changes neither the arithmetic nor its order
-// (only S does), so it is free to vary with N, the shard size and the device.
-struct Shape { int pairs, threads; float efficiency; };
-constexpr Shape kShapes[6] = {{4, 256, 0.763f}, {4, 128, 0.753f}, {2, 128, 0.754f},
-                              {2, 64, 0.734f},  {1, 64, 0.728f},  {1, 32, 0.722f}};
-
+// launch shape for a step (csrc/step_layout.hpp), with the canonical S of the sources and the forced
+// shape of the switches
 Plan make_plan(int n_targets, int n_sources, int sm_count, const Switches &sw)
 {
-    const int S = mapc_plan_segments((uint32_t)n_sources);
-    Plan best{1, 32, 0, S};
-    float best_score = -1.f;
-    const int fp = sw.plan_pairs, ft = sw.plan_threads;
-    for (const Shape &sh : kShapes) {
-        if ((fp && fp != sh.pairs) || (ft && ft != sh.threads)) continue;
-        const int per_block = sh.threads * 2 * sh.pairs;
-        const int bx = (n_targets + per_block - 1) / per_block;
-        if (bx == 0) continue;
-        const double used = (double)n_targets / ((double)bx * per_block);            // busy target lanes
-        const double blocks_per_sm = (double)bx * S / sm_count;
-        const double warps_per_smsp = blocks_per_sm * (sh.threads / 32) / 4.0;
-        const double bal_block = blocks_per_sm / std::ceil(blocks_per_sm);
-        const double bal_warp = warps_per_smsp / std::ceil(warps_per_smsp);
-        const float score = (float)(sh.efficiency * used * std::min(bal_block, bal_warp));
-        if (score > best_score) {
-            best_score = score;
-            best = Plan{sh.pairs, sh.threads, bx, S};
-        }
-    }
-    return best;
+    return mapc::make_plan(n_targets, mapc_plan_segments((uint32_t)n_sources), sm_count, sw.plan_pairs,
+                           sw.plan_threads);
 }
 
 }  // namespace
@@ -603,13 +573,7 @@ mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::Step
 // targets of this shard that a Simulate(n_active) updates, as a count from i_first
 int local_targets(const mapc_compute *c, int n_active)
 {
-    if (n_active <= 0) return 0;
-    long long t = ((long long)n_active + MAPC_BLOCK_SIZE - 1) / MAPC_BLOCK_SIZE * MAPC_BLOCK_SIZE;
-    if (t > c->n) t = c->n;  // Dispatch(ceil(n/64)) (Compute.cpp:1041); OOB writes are dropped
-    long long loc = t - (long long)c->i_first;
-    if (loc < 0) loc = 0;
-    if (loc > c->n_local) loc = c->n_local;
-    return (int)loc;
+    return mapc::local_targets(c->n, c->i_first, c->n_local, n_active);
 }
 
 mapc_status ensure_partial(mapc_compute *c, int segments)
@@ -1062,18 +1026,12 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             args.stamp_end = c->stamp_end_next;       // every launch: whichever finishes the step writes it
             args.fence_word = c->fence_write_next ? (unsigned long long *)c->fence->word : nullptr;
             args.fence_value = c->fence_write_next;
-            mapc::SegList local{0, {}}, remote{0, {}};
-            int owner[MAPC_MAX_SEGMENTS];
-            bool peer = c->peer_mode && fuse && n_sources == (int)c->n && sw.peer && !sw.mass_in_loop && !sw.chunk;
-            for (int s = 0; s < pl.segments; ++s) {
-                int j0, j1;
-                mapc::segment_range(n_sources, pl.segments, s, j0, j1);
-                const bool inside = j0 >= (int)c->i_first && j1 <= (int)(c->i_first + c->n_local);
-                owner[s] = j1 > j0 ? j0 / (int)c->n_local : c->rank;
-                if (j1 > j0 && (j1 - 1) / (int)c->n_local != owner[s]) peer = false;  // straddles two shards
-                const bool is_local = c->world == 1 || inside || (!c->peer_mode && !c->gather_pending[r]);
-                (is_local ? local : remote).ids[(is_local ? local : remote).count++] = s;
-            }
+            const mapc::StepLayout lay = mapc::classify_segments(n_sources, pl.segments, (int)c->i_first, (int)c->n_local,
+                                                                 c->rank, c->world, c->peer_mode, c->gather_pending[r]);
+            const mapc::SegList &local = lay.local, &remote = lay.remote;
+            const int *owner = lay.owner;
+            const bool peer = c->peer_mode && fuse && n_sources == (int)c->n && sw.peer && !sw.mass_in_loop &&
+                              !sw.chunk && lay.aligned;
             if (c->peer_mode && !peer && remote.count > 0 && !c->gather_pending[r]) {
                 // exchange falls back to NCCL for this step, but the read side was never gathered
                 return fail(MAPC_ERR_UNSUPPORTED, "peer exchange attached but this step's segments do not align "

@@ -1,0 +1,99 @@
+// step_layout.hpp -- the pure host-side decisions of one all-pairs step: which targets a Simulate(n_active)
+// updates on a shard, which launch shape (P, T) runs them, and which canonical segments a rank evaluates at
+// once (their sources are resident) or after the exchange (remote).  No CUDA calls: csrc/mapc.cu applies the
+// result to streams and kernels, tests/emu/emu_kernels.cpp applies the very same functions to the emulated
+// kernels, so the CPU suite exercises this logic too.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+
+#include "nbody_kernels.cuh"
+
+namespace mapc {
+
+struct Plan {
+    int pairs;    // P: register pairs per thread (2P targets per thread)
+    int threads;  // T
+    int blocks_x; // target blocks of T*2P bodies
+    int segments; // canonical S
+};
+
+// Launch shapes (P, T) with the FMA-pipe efficiency each reaches at large N (tools/ubench,
+// profiles/): all sit on the same 67-72 % plateau, so at large N the choice barely matters, while
+// at small N what decides is how evenly the cells fall on the 4 x SMs warp schedulers and how many
+// target lanes the last block leaves idle.  The shape changes neither the arithmetic nor its order
+// (only S does), so it is free to vary with N, the shard size and the device.
+struct Shape { int pairs, threads; float efficiency; };
+constexpr Shape kShapes[6] = {{4, 256, 0.763f}, {4, 128, 0.753f}, {2, 128, 0.754f},
+                              {2, 64, 0.734f},  {1, 64, 0.728f},  {1, 32, 0.722f}};
+
+// S = mapc_plan_segments(n_sources); force_pairs / force_threads != 0 pin the shape (MAPC_PLAN_PAIRS / _THREADS)
+inline Plan make_plan(int n_targets, int S, int sm_count, int force_pairs, int force_threads)
+{
+    Plan best{1, 32, 0, S};
+    float best_score = -1.f;
+    for (const Shape &sh : kShapes) {
+        if ((force_pairs && force_pairs != sh.pairs) || (force_threads && force_threads != sh.threads)) continue;
+        const int per_block = sh.threads * 2 * sh.pairs;
+        const int bx = (n_targets + per_block - 1) / per_block;
+        if (bx == 0) continue;
+        const double used = (double)n_targets / ((double)bx * per_block);            // busy target lanes
+        const double blocks_per_sm = (double)bx * S / sm_count;
+        const double warps_per_smsp = blocks_per_sm * (sh.threads / 32) / 4.0;
+        const double bal_block = blocks_per_sm / std::ceil(blocks_per_sm);
+        const double bal_warp = warps_per_smsp / std::ceil(warps_per_smsp);
+        const float score = (float)(sh.efficiency * used * std::min(bal_block, bal_warp));
+        if (score > best_score) {
+            best_score = score;
+            best = Plan{sh.pairs, sh.threads, bx, S};
+        }
+    }
+    return best;
+}
+
+// targets of the shard [i_first, i_first + n_local) that a Simulate(n_active) updates, as a count from
+// i_first: Dispatch(ceil(n/64)) groups of 64 threads (Compute.cpp:1041); writes past N are dropped
+inline int local_targets(uint32_t n, uint32_t i_first, uint32_t n_local, int n_active)
+{
+    if (n_active <= 0) return 0;
+    long long t = ((long long)n_active + MAPC_BLOCK_SIZE - 1) / MAPC_BLOCK_SIZE * MAPC_BLOCK_SIZE;
+    if (t > (long long)n) t = n;
+    long long loc = t - (long long)i_first;
+    if (loc < 0) loc = 0;
+    if (loc > (long long)n_local) loc = n_local;
+    return (int)loc;
+}
+
+// Which canonical segments a rank can evaluate straight away and which must wait for the exchange.
+//   local   every segment of an unsharded handle; on a shard the segments whose sources all lie inside it
+//           (the rank wrote them itself); and, without a peer exchange, everything while no gather of the read
+//           side is outstanding (right after an upload every rank holds all N positions)
+//   remote  the rest: second launch, after the all-gather or through the owners' memory
+//   owner[s]   rank whose shard holds segment s (a segment never counts as owned by two)
+//   aligned    no segment straddles two shards (what the peer exchange needs)
+struct StepLayout {
+    SegList local, remote;
+    int owner[MAPC_MAX_SEGMENTS];
+    bool aligned;
+};
+
+inline StepLayout classify_segments(int n_sources, int S, int i_first, int n_local, int rank, int world,
+                                    bool peer_mode, bool gather_pending)
+{
+    StepLayout out{};
+    out.aligned = true;
+    for (int s = 0; s < S; ++s) {
+        int j0, j1;
+        segment_range(n_sources, S, s, j0, j1);
+        const bool inside = j0 >= i_first && j1 <= i_first + n_local;
+        out.owner[s] = j1 > j0 ? j0 / n_local : rank;
+        if (j1 > j0 && (j1 - 1) / n_local != out.owner[s]) out.aligned = false;  // straddles two shards
+        const bool is_local = world == 1 || inside || (!peer_mode && !gather_pending);
+        SegList &list = is_local ? out.local : out.remote;
+        list.ids[list.count++] = s;
+    }
+    return out;
+}
+
+}  // namespace mapc

@@ -9,6 +9,7 @@
 // MIRRORED flavour.  Built by tests/emu/Makefile with g++ -ffp-contract=off; never linked into libmapc.so.
 #define MAPC_HOST_EMULATION 1
 #include "../../multi-adapter-particles_b200/csrc/nbody_kernels.cuh"
+#include "../../multi-adapter-particles_b200/csrc/step_layout.hpp"
 
 #include <sched.h>
 
@@ -57,18 +58,6 @@ bool launch_force(int pairs, int threads, bool fuse, bool peer, bool inloop, int
     return false;
 }
 
-// csrc/mapc.cu local_targets(): Dispatch(ceil(n_active/64)) groups of 64, clipped to the shard
-int local_targets(int n, int i_first, int n_local, int n_active)
-{
-    if (n_active <= 0) return 0;
-    long long t = ((long long)n_active + MAPC_BLOCK_SIZE - 1) / MAPC_BLOCK_SIZE * MAPC_BLOCK_SIZE;
-    if (t > n) t = n;
-    long long loc = t - i_first;
-    if (loc < 0) loc = 0;
-    if (loc > n_local) loc = n_local;
-    return (int)loc;
-}
-
 struct alignas(16) PV { float pos[4]; float velo[4]; };
 static_assert(sizeof(PV) == sizeof(mapc_posvelo), "PosVelo layout");
 
@@ -106,7 +95,7 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
 
     for (int r = 0; r < world; ++r) {
         const int i_first = r * n_local;
-        const int n_targets = local_targets(n, i_first, n_local, n_active);
+        const int n_targets = mapc::local_targets((uint32_t)n, (uint32_t)i_first, (uint32_t)n_local, n_active);
         if (n_targets <= 0) continue;
         const int per_block = threads * 2 * pairs;
         std::vector<PV> in_local(n_local), out_local(n_local);
@@ -139,18 +128,13 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
         a.fence_word = (fuse && world == 1) ? &fence_word : nullptr;
         a.fence_value = 42;
 
-        mapc::SegList local{0, {}}, remote{0, {}};
-        int owner[MAPC_MAX_SEGMENTS];
-        bool peer_ok = peer && fuse && n_sources == n && !mass_in_loop && chunk == 0;
-        for (int s = 0; s < S; ++s) {
-            int j0, j1;
-            mapc::segment_range(n_sources, S, s, j0, j1);
-            const bool inside = j0 >= i_first && j1 <= i_first + n_local;
-            owner[s] = j1 > j0 ? j0 / n_local : r;
-            if (j1 > j0 && (j1 - 1) / n_local != owner[s]) peer_ok = false;
-            const bool is_local = world == 1 || inside;
-            (is_local ? local : remote).ids[(is_local ? local : remote).count++] = s;
-        }
+        // csrc/step_layout.hpp, the function csrc/mapc.cu uses: with the NCCL layout the emulated step is the
+        // steady state (a gather of the read side is outstanding, so only the shard's own segments are local)
+        const mapc::StepLayout lay = mapc::classify_segments(n_sources, S, i_first, n_local, r, world, peer != 0,
+                                                             /*gather_pending=*/world > 1 && !peer);
+        const mapc::SegList &local = lay.local, &remote = lay.remote;
+        const int *owner = lay.owner;
+        const bool peer_ok = peer && fuse && n_sources == n && !mass_in_loop && chunk == 0 && lay.aligned;
         if (peer && world > 1 && !peer_ok && remote.count > 0) return -2;
 
         a.segs = local;
@@ -196,7 +180,7 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
 int emu_step_well(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next_out, float *packed_out, int n,
                   int n_active, float dt, float damping, int i_first, int n_local)
 {
-    const int n_targets = local_targets(n, i_first, n_local, n_active);
+    const int n_targets = mapc::local_targets((uint32_t)n, (uint32_t)i_first, (uint32_t)n_local, n_active);
     std::vector<PV> in_local(n_local), out_local(n_local);
     std::memcpy(in_local.data(), in + i_first, (size_t)n_local * sizeof(PV));
     std::memcpy(out_local.data(), out + i_first, (size_t)n_local * sizeof(PV));
@@ -217,6 +201,18 @@ int emu_step_well(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next_out
     std::memcpy(pos_next_out, pos_next.data(), (size_t)n * 16);
     std::memcpy(packed_out, packed.data(), (size_t)n * 16);
     return 0;
+}
+
+// csrc/step_layout.hpp make_plan / local_targets, for the host-logic tests: out = {pairs, threads, blocks_x, S}
+void emu_make_plan(int n_targets, int S, int sm_count, int force_pairs, int force_threads, int *out)
+{
+    const mapc::Plan pl = mapc::make_plan(n_targets, S, sm_count, force_pairs, force_threads);
+    out[0] = pl.pairs; out[1] = pl.threads; out[2] = pl.blocks_x; out[3] = pl.segments;
+}
+
+int emu_local_targets(unsigned n, unsigned i_first, unsigned n_local, int n_active)
+{
+    return mapc::local_targets(n, i_first, n_local, n_active);
 }
 
 }  // extern "C"

@@ -31,6 +31,10 @@ def emu():
     vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     lib.emu_step_allpairs.restype = ci
     lib.emu_step_allpairs.argtypes = [vp, vp, vp, ci, ci, cf, cf, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+    lib.emu_make_plan.restype = None
+    lib.emu_make_plan.argtypes = [ci, ci, ci, ci, ci, vp]
+    lib.emu_local_targets.restype = ci
+    lib.emu_local_targets.argtypes = [ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ci]
     lib.emu_step_well.restype = ci
     lib.emu_step_well.argtypes = [vp, vp, vp, vp, ci, ci, cf, cf, ci, ci]
     return lib
@@ -272,3 +276,31 @@ def test_emulated_kernel_trajectory_against_golden(emu, oracle, mapc, name):
         if step == 1:
             assert max(oracle.rel_errors(state, g["literal_1"]).values()) <= 1e-5
     assert max(oracle.rel_errors(state, g["literal_last"]).values()) <= 1e-4
+
+
+def test_launch_plan_and_dispatch_granularity(emu, oracle, mapc):
+    """csrc/step_layout.hpp (shared by csrc/mapc.cu and the emulation): the launch shape chosen for the
+    BASELINE sizes, forced shapes, and the number of targets a Simulate(n_active) updates on a shard."""
+    def plan(n_targets, S, force=(0, 0), sms=148):
+        out = (ctypes.c_int * 4)()
+        emu.emu_make_plan(n_targets, S, sms, force[0], force[1], out)
+        return tuple(out)
+
+    # config 3: 262,144 targets, S = 32 -> (4, 256), 128 target blocks x 32 segments = 4,096 cells
+    assert plan(262_144, 32) == (4, 256, 128, 32)
+    # an 8-GPU shard of the weak-scaled size: 92,672 targets are exactly 181 blocks of (2, 128), which beats
+    # the 1.6 % of idle lanes (4, 256) would leave in its 46th block
+    assert plan(92_672, 128) == (2, 128, 181, 128)
+    # every shape can be forced, and covers all targets
+    for pairs, threads in SHAPES:
+        pl = plan(10_000, 32, (pairs, threads))
+        assert pl[:2] == (pairs, threads) and pl[2] * pairs * 2 * threads >= 10_000 > (pl[2] - 1) * pairs * 2 * threads
+    # a single target still gets a block
+    assert plan(1, 32)[2] == 1
+    # dispatch granularity (Compute.cpp:1041) agrees with the oracle's statement of it
+    for n, n_active in ((1000, 0), (1000, 1), (1000, 64), (1000, 65), (1000, 999), (1000, 1000), (10_000, 9_999)):
+        assert emu.emu_local_targets(n, 0, n, n_active) == oracle.num_targets(n, n_active)
+    # on the second of two shards of 512: targets past the shard start only
+    assert emu.emu_local_targets(1024, 512, 512, 100) == 0
+    assert emu.emu_local_targets(1024, 512, 512, 600) == 128
+    assert emu.emu_local_targets(1024, 512, 512, 1024) == 512
