@@ -72,4 +72,6 @@ def test_experimental_bounded_chain_order(mapc, oracle, gpu):
     mir = oracle.step_allpairs(p, flavour=oracle.MIRRORED, chunk=2048)
     err_l, err_m = oracle.rel_errors(chunked, lit), oracle.rel_errors(chunked, mir)
     print("MAPC_CHUNK=1 vs chunked oracle: literal", err_l, "mirrored", err_m)
-    assert max(err_l.values()) <= TOL_1 and max(err_m.values()) <= 3e-6, (err_l, err_m)
+    # both at the 1e-5 gate: over ALL targets the distance to MIRRORED is set by the same chain noise as the
+    # distance to LITERAL (MUFU.RSQ perturbs every term, after which the roundings of the chain decorrelate)
+    assert max(err_l.values()) <= TOL_1 and max(err_m.values()) <= TOL_1, (err_l, err_m)
