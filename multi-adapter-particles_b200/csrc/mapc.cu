@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>  // declarations only: libnccl is dlopen()ed when a sharded handle is created
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges are emitted only with MAPC_NVTX=1
 #include <sched.h>
 
 #include <chrono>
@@ -133,6 +134,22 @@ struct DeviceGuard {
     ~DeviceGuard()
     {
         if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Named ranges for timelines (the reference labels its D3D12 objects for PIX, Compute.cpp:428-472): off by
+// default so the per-call path stays as measured; MAPC_NVTX=1 (read once) brackets the entry points below.
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char *name)
+    {
+        static const bool enabled = [] { const char *v = getenv("MAPC_NVTX"); return v && *v && atoi(v) != 0; }();
+        on = enabled;
+        if (on) nvtxRangePushA(name);
+    }
+    ~NvtxRange()
+    {
+        if (on) nvtxRangePop();
     }
 };
 
@@ -872,6 +889,7 @@ mapc_status mapc_compute_destroy(mapc_compute *c)
 // ---- state in / out ---------------------------------------------------------------------------
 mapc_status mapc_compute_upload(mapc_compute *c, const mapc_posvelo *host, uint32_t n)
 {
+    NvtxRange range("mapc: Upload");
     if (!c || !host) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (n != c->n) return fail(MAPC_ERR_INVALID_ARGUMENT, "upload of %u bodies into a handle of %u", n, c->n);
     MAPC_TRY(mapc::require_ungated(&c->gcompute, "Upload"));
@@ -902,6 +920,7 @@ mapc_status mapc_compute_upload(mapc_compute *c, const mapc_posvelo *host, uint3
 
 mapc_status mapc_compute_download(mapc_compute *c, mapc_posvelo *host, uint32_t first, uint32_t count)
 {
+    NvtxRange range("mapc: Download");
     if (!c || !host) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (first < c->i_first || (uint64_t)first + count > (uint64_t)c->i_first + c->n_local)
         return fail(MAPC_ERR_INVALID_ARGUMENT, "range [%u, %u) outside shard [%u, %u)", first,
@@ -1115,6 +1134,7 @@ mapc_status mapc_compute_simulate(mapc_compute *c, int num_active_particles, flo
 mapc_status mapc_compute_simulate_steps(mapc_compute *c, int num_active_particles, float delta_time,
                                         float damping, uint64_t consumer_fence_value, int steps)
 {
+    NvtxRange range("mapc: Simulate");
     if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
     if (steps < 1) return fail(MAPC_ERR_INVALID_ARGUMENT, "steps must be >= 1");
     if (num_active_particles < 0 || (uint32_t)num_active_particles > c->n)
@@ -1311,6 +1331,7 @@ mapc_status mapc_compute_flush(mapc_compute *c)
 
 mapc_status mapc_compute_copy_state(mapc_compute *dst, mapc_compute *src)
 {
+    NvtxRange range("mapc: CopyState");
     if (!dst || !src) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
     if (dst->n != src->n || dst->i_first != src->i_first || dst->n_local != src->n_local)
         return fail(MAPC_ERR_INVALID_ARGUMENT, "copy_state between different shapes (%u/%u vs %u/%u)",
@@ -1541,6 +1562,7 @@ mapc_status mapc_consumer_create(mapc_consumer **out, mapc_compute *producer, in
 mapc_status mapc_consumer_draw(mapc_consumer *r, int num_active_particles, uint64_t *inout_fence_value,
                                int num_particles_copied)
 {
+    NvtxRange range("mapc: consumer Draw");
     if (!r || !inout_fence_value) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!r->producer) return fail(MAPC_ERR_INVALID_ARGUMENT, "the producer of this consumer has been destroyed");
     if (num_active_particles < 0 || (uint32_t)num_active_particles > r->n || num_particles_copied < 0 ||
