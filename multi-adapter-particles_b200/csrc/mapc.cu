@@ -89,6 +89,7 @@ struct NcclApi {
     decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     decltype(&ncclGetVersion) GetVersion = nullptr;
+    decltype(&ncclCommGetAsyncError) CommGetAsyncError = nullptr;   // optional
 } g_nccl;
 
 mapc_status load_nccl()
@@ -112,6 +113,7 @@ mapc_status load_nccl()
     MAPC_SYM(GetErrorString, "ncclGetErrorString");
     MAPC_SYM(GetVersion, "ncclGetVersion");
 #undef MAPC_SYM
+    g_nccl.CommGetAsyncError = (decltype(g_nccl.CommGetAsyncError))dlsym(lib, "ncclCommGetAsyncError");
     g_nccl.lib = lib;
     return MAPC_OK;
 }
@@ -1190,6 +1192,14 @@ mapc_status mapc_compute_wait_for_gpu(mapc_compute *c)
     MAPC_TRY(mapc::require_ungated(&c->gcompute, "WaitForGpu"));
     MAPC_CUDA(cudaStreamSynchronize(c->compute));
     MAPC_CUDA(cudaStreamSynchronize(c->comm));
+    if (c->nccl && g_nccl.CommGetAsyncError) {
+        // a collective that failed asynchronously (a peer died, a link error) must not pass as a finished step
+        ncclResult_t async = ncclSuccess;
+        const ncclResult_t q = g_nccl.CommGetAsyncError(c->nccl, &async);
+        if (q != ncclSuccess || (async != ncclSuccess && async != ncclInProgress))
+            return fail(MAPC_ERR_NCCL, "NCCL communicator reports an asynchronous error: %s",
+                        g_nccl.GetErrorString(q != ncclSuccess ? q : async));
+    }
     if (mapc_fence_completed_value(c->fence) < v)
         return fail(MAPC_ERR_CUDA, "fence at %llu after drain, expected >= %llu",
                     (unsigned long long)mapc_fence_completed_value(c->fence), (unsigned long long)v);
