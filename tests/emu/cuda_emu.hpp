@@ -5,7 +5,8 @@
 // REAL kernel source -- indexing, staging, ragged tails, segment lists, arrival counters, fused combine +
 // integrate -- and compare it bit for bit with the oracle's MIRRORED flavour.  What it cannot show is
 // anything the hardware adds: MUFU.RSQ's rounding (emulated as the correctly rounded 1/sqrt the MIRRORED
-// flavour uses), warp scheduling, memory-model races between concurrently resident blocks, PDL, TMA.
+// flavour uses), warp scheduling, memory-model races between concurrently resident blocks, PDL, and the real
+// asynchrony of TMA (the bulk copy is a memcpy here; what IS checked is its addresses, sizes and phase logic).
 // Nothing outside tests/ includes this file; the product build never defines MAPC_HOST_EMULATION.
 #pragma once
 
@@ -14,6 +15,7 @@
 #include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 #include <time.h>
 
 #include <functional>
@@ -42,7 +44,9 @@ struct dim3 {
 // ---- built-in variables: per emulated thread ---------------------------------------------------------------
 namespace cuda_emu {
 struct Block {
-    pthread_barrier_t barrier;
+    pthread_barrier_t barrier;            // __syncthreads()
+    pthread_barrier_t warp_barrier[32];   // one per warp of the block, for the shuffle emulation
+    float xchg[32][32];                   // [warp][lane]: values being shuffled
 };
 extern thread_local uint3 t_threadIdx, t_blockIdx;
 extern thread_local dim3 t_blockDim, t_gridDim;
@@ -71,8 +75,19 @@ static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetc
 template <class T> static inline T __ldcg(const T *p) { return *p; }
 static inline void __nanosleep(unsigned) { sched_yield(); }
 static inline size_t __cvta_generic_to_shared(const void *p) { return (size_t)p; }
-// warp shuffles need lock-step lanes, which this emulation does not have: the SHFL variant is not emulated
-static inline float __shfl_sync(unsigned, float, int) { abort(); }
+// Warp shuffle: the 32 OS threads of a warp meet at a per-warp barrier, publish their values, read the source
+// lane's, and meet again before the slots are reused.  Every lane of the warp must execute the shuffle (true of
+// the SHFL staging variant: a uniform loop over the 64-body tile).
+static inline float __shfl_sync(unsigned, float v, int src_lane)
+{
+    cuda_emu::Block *b = cuda_emu::t_block;
+    const unsigned w = cuda_emu::t_threadIdx.x / 32, lane = cuda_emu::t_threadIdx.x % 32;
+    b->xchg[w][lane] = v;
+    pthread_barrier_wait(&b->warp_barrier[w]);
+    const float r = b->xchg[w][src_lane & 31];
+    pthread_barrier_wait(&b->warp_barrier[w]);
+    return r;
+}
 
 // ---- stand-ins for the PTX of nbody_kernels.cuh -----------------------------------------------------------------
 namespace mapc {
@@ -85,12 +100,30 @@ static inline unsigned long long global_timer_ns()
     return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
 }
 static inline unsigned smem_u32(const void *) { return 0; }
-// TMA staging is not emulated (template flag TMA = false everywhere in tests/emu)
-static inline void mbar_init(unsigned long long *, unsigned) { abort(); }
-static inline void mbar_expect_tx(unsigned long long *, unsigned) { abort(); }
-static inline void mbar_wait(unsigned long long *, unsigned) { abort(); }
-static inline void tma_load_1d(void *, const void *, unsigned, unsigned long long *) { abort(); }
-static inline void fence_mbarrier_init() { abort(); }
+// 1-D TMA staging: the mbarrier word counts completed phases.  The kernel arms a phase with one arrival
+// (expect_tx by the issuing thread) and completes it with the bulk copy's bytes, so here the copy itself
+// (a memcpy) completes the phase; a waiter for parity P spins until the current phase's parity differs from
+// P.  Bytes must be what the hardware accepts: a non-zero multiple of 16, both addresses 16-byte aligned.
+static inline void mbar_init(unsigned long long *bar, unsigned count)
+{
+    if (count != 1) abort();
+    __atomic_store_n(bar, 0ull, __ATOMIC_RELEASE);
+}
+static inline void mbar_expect_tx(unsigned long long *, unsigned bytes)
+{
+    if (bytes == 0 || bytes % 16 != 0) abort();
+}
+static inline void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1ull) == (unsigned long long)(parity & 1u)) sched_yield();
+}
+static inline void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    if (bytes == 0 || bytes % 16 != 0 || ((uintptr_t)smem_dst & 15) || ((uintptr_t)gmem_src & 15)) abort();
+    memcpy(smem_dst, gmem_src, bytes);
+    __atomic_fetch_add(bar, 1ull, __ATOMIC_RELEASE);
+}
+static inline void fence_mbarrier_init() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline unsigned long long load_acquire_sys(const unsigned long long *p)
 {
     return __atomic_load_n(p, __ATOMIC_ACQUIRE);
@@ -141,12 +174,18 @@ inline void launch(dim3 grid, dim3 block, int order, const std::function<void()>
     pthread_attr_setstacksize(&attr, 256 * 1024);
     Block blk;
     pthread_barrier_init(&blk.barrier, nullptr, nthreads);
+    const unsigned nwarps = (nthreads + 31) / 32;
+    for (unsigned w = 0; w < nwarps; ++w) {
+        const unsigned lanes = (w + 1) * 32 <= nthreads ? 32 : nthreads - w * 32;
+        pthread_barrier_init(&blk.warp_barrier[w], nullptr, lanes);
+    }
     for (unsigned t = 0; t < nthreads; ++t) {
         ctx[t] = ThreadCtx{&body, t, block, grid, order, &blk};
         if (pthread_create(&th[t], &attr, thread_main, &ctx[t]) != 0) abort();
     }
     for (unsigned t = 0; t < nthreads; ++t) pthread_join(th[t], nullptr);
     pthread_barrier_destroy(&blk.barrier);
+    for (unsigned w = 0; w < nwarps; ++w) pthread_barrier_destroy(&blk.warp_barrier[w]);
     pthread_attr_destroy(&attr);
     delete[] th;
     delete[] ctx;

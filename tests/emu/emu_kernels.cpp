@@ -28,10 +28,22 @@ namespace {
 using mapc::StepArgs;
 
 template <int P, int T, int TJ, int U, int MINB, int ORDER>
-bool launch_shape(bool fuse, bool peer, bool inloop, int chunk, const StepArgs &a, int order)
+bool launch_shape(bool fuse, bool peer, bool inloop, int chunk, int staging, bool has_tma, const StepArgs &a, int order)
 {
     const dim3 grid((unsigned)a.n_iblocks, (unsigned)a.segs.count, 1), block(T, 1, 1);
     if (a.segs.count == 0 || a.i_cnt <= 0) return true;
+    if (staging != 0) {
+        // MAPC_TMA=1 / MAPC_SHFL=1: like csrc/mapc.cu, for the fused, non-peer, mass-per-partial kernel only;
+        // TMA staging exists for the 256-body-stage shapes
+        if (!fuse || peer || inloop || chunk != 0) return false;
+        if (staging == 1) {
+            if (!has_tma) return false;
+            cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, false, true>(a); });
+        } else {
+            cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, false, false, false, true>(a); });
+        }
+        return true;
+    }
     if (chunk != 0) {
         // MAPC_CHUNK=1: csrc/mapc.cu has it for the fused, non-peer, mass-per-partial kernel only, with
         // 2,048-source chunks; 256 is instantiated here as well so that small problems have several chunks
@@ -49,10 +61,12 @@ bool launch_shape(bool fuse, bool peer, bool inloop, int chunk, const StepArgs &
     return true;
 }
 
-bool launch_force(int pairs, int threads, bool fuse, bool peer, bool inloop, int chunk, const StepArgs &a, int order)
+bool launch_force(int pairs, int threads, bool fuse, bool peer, bool inloop, int chunk, int staging, const StepArgs &a,
+                  int order)
 {
 #define MAPC_SHAPE(P, T, TJ, U, MINB, ORDER, HAS_TMA) \
-    if (pairs == P && threads == T) return launch_shape<P, T, TJ, U, MINB, ORDER>(fuse, peer, inloop, chunk, a, order);
+    if (pairs == P && threads == T)                   \
+        return launch_shape<P, T, TJ, U, MINB, ORDER>(fuse, peer, inloop, chunk, staging, HAS_TMA, a, order);
 #include "../../multi-adapter-particles_b200/csrc/force_shapes.inc"
 #undef MAPC_SHAPE
     return false;
@@ -70,11 +84,12 @@ extern "C" {
 // .. world-1 wrote it (own shards only).  info[0] = kernel launches, info[1] = fence word after the step,
 // info[2] = 1 if every arrival counter and the `done` counter were back at zero.
 // chunk: 0, or the CHUNK template value (sources per bounded chain: 256 or 2048).
+// staging: 0 LDG/STS + LDS broadcast (default), 1 TMA bulk copies (MAPC_TMA=1), 2 warp-shuffle broadcast (MAPC_SHFL=1).
 // returns 0, or -1 for an unknown shape / variant, -2 for a layout the library would refuse (peer with
 // straddling segments)
 int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next_out, int n, int n_active,
                       float dt, float damping, int S, int pairs, int threads, int fuse, int mass_in_loop,
-                      int world, int peer, int block_order, int chunk, unsigned long long *info)
+                      int world, int peer, int block_order, int chunk, int staging, unsigned long long *info)
 {
     if (n % world) return -2;
     const int n_local = n / world;
@@ -138,7 +153,7 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
         if (peer && world > 1 && !peer_ok && remote.count > 0) return -2;
 
         a.segs = local;
-        if (!launch_force(pairs, threads, fuse, false, mass_in_loop, chunk, a, block_order)) return -1;
+        if (!launch_force(pairs, threads, fuse, false, mass_in_loop, chunk, staging, a, block_order)) return -1;
         launches += (local.count > 0);
         if (local.count > 0) a.stamp_begin = nullptr;
         if (remote.count > 0) {
@@ -151,7 +166,7 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
                 }
                 a.flag_expect = 7;
             }
-            if (!launch_force(pairs, threads, fuse, use_peer, mass_in_loop, chunk, a, block_order)) return -1;
+            if (!launch_force(pairs, threads, fuse, use_peer, mass_in_loop, chunk, use_peer ? 0 : staging, a, block_order)) return -1;
             ++launches;
         }
         if (!fuse) {

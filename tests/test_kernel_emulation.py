@@ -30,7 +30,7 @@ def emu():
     lib = ctypes.CDLL(os.path.join(EMU_DIR, "libmapc_emu.so"))
     vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     lib.emu_step_allpairs.restype = ci
-    lib.emu_step_allpairs.argtypes = [vp, vp, vp, ci, ci, cf, cf, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+    lib.emu_step_allpairs.argtypes = [vp, vp, vp, ci, ci, cf, cf, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
     lib.emu_make_plan.restype = None
     lib.emu_make_plan.argtypes = [ci, ci, ci, ci, ci, vp]
     lib.emu_local_targets.restype = ci
@@ -41,7 +41,7 @@ def emu():
 
 
 def emu_step(lib, particles, S, shape, n_active=None, dt=0.1, damping=1.0, fuse=True, mass_in_loop=False,
-             world=1, peer=False, block_order=0, stale=None, chunk=0):
+             world=1, peer=False, block_order=0, stale=None, chunk=0, staging=0):
     """-> (written side, packed mirror, info) after one emulated step."""
     n = particles.shape[0]
     n_active = n if n_active is None else n_active
@@ -51,7 +51,7 @@ def emu_step(lib, particles, S, shape, n_active=None, dt=0.1, damping=1.0, fuse=
     info = np.zeros(3, dtype=np.uint64)
     rc = lib.emu_step_allpairs(inp.ctypes.data, out.ctypes.data, mirror.ctypes.data, n, n_active, dt, damping, S,
                                shape[0], shape[1], int(fuse), int(mass_in_loop), world, int(peer), block_order,
-                               chunk, info.ctypes.data)
+                               chunk, staging, info.ctypes.data)
     assert rc == 0, f"emu_step_allpairs returned {rc}"
     return out, mirror, info
 
@@ -304,3 +304,31 @@ def test_launch_plan_and_dispatch_granularity(emu, oracle, mapc):
     assert emu.emu_local_targets(1024, 512, 512, 100) == 0
     assert emu.emu_local_targets(1024, 512, 512, 600) == 128
     assert emu.emu_local_targets(1024, 512, 512, 1024) == 512
+
+
+TMA, SHFL = 1, 2
+
+
+@pytest.mark.parametrize("shape", [(4, 256), (4, 128), (2, 128)])
+def test_tma_staging_variant_bitwise(emu, oracle, mapc, shape):
+    """MAPC_TMA=1: the stages filled by 1-D bulk copies + mbarrier phases instead of LDG/STS (the shapes with
+    256-body stages).  Emulated as memcpy + phase counter: checks the copy's source offsets, byte counts
+    (a non-zero multiple of 16, 16-byte aligned -- what cp.async.bulk accepts) and the double-buffer parity."""
+    n = 1100
+    p = mapc.ic.plummer(n, 80.0, seed=5)
+    for S in (1, 2, 32):
+        got, mirror, info = emu_step(emu, p, S, shape, staging=TMA)
+        ref = oracle_step(oracle, p, S)
+        assert got.tobytes() == ref.tobytes(), S
+        assert mirror.tobytes() == ref["pos"].tobytes() and info[2] == 1
+
+
+@pytest.mark.parametrize("shape", [(2, 128), (1, 64), (1, 32)])
+def test_shuffle_broadcast_variant_bitwise(emu, oracle, mapc, shape):
+    """MAPC_SHFL=1: each lane reads one body of a 32-body group and the group is handed round with warp
+    shuffles (emulated with per-warp barriers).  Same bodies in the same order: same bits."""
+    n = 200
+    p = mapc.ic.uniform_sphere(n, 100.0, seed=17, speed=1.0)
+    for S in (1, 32):
+        got, _, _ = emu_step(emu, p, S, shape, staging=SHFL)
+        assert got.tobytes() == oracle_step(oracle, p, S).tobytes(), S
