@@ -332,3 +332,28 @@ def test_shuffle_broadcast_variant_bitwise(emu, oracle, mapc, shape):
     for S in (1, 32):
         got, _, _ = emu_step(emu, p, S, shape, staging=SHFL)
         assert got.tobytes() == oracle_step(oracle, p, S).tobytes(), S
+
+
+def test_fuzz_emulated_kernel_against_oracle(emu, oracle, mapc):
+    """Property-based sweep (hypothesis): any N, any segment count, any launch shape, any n_active, fused or
+    not, with or without bounded chains -- the emulated kernel equals the oracle's MIRRORED flavour bit for bit
+    and leaves the bodies it does not dispatch untouched."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(n=st.integers(1, 700), S=st.integers(1, 40), shape=st.sampled_from(SHAPES),
+           frac=st.floats(0.0, 1.0), fuse=st.booleans(), chunk=st.sampled_from([0, 0, 256]),
+           seed=st.integers(0, 1000))
+    def check(n, S, shape, frac, fuse, chunk, seed):
+        if chunk and not fuse:
+            chunk = 0
+        n_active = max(1, min(n, int(round(frac * n)))) if frac < 0.9 else n
+        p = mapc.ic.uniform_sphere(n, 150.0, seed=seed, speed=1.0)
+        stale = p.copy()
+        stale["velo"] -= 2.0
+        got, _, info = emu_step(emu, p, S, shape, n_active=n_active, fuse=fuse, stale=stale, chunk=chunk,
+                                dt=0.07, damping=0.99)
+        ref = oracle_step(oracle, p, S, n_active=n_active, stale=stale, chunk=chunk, dt=0.07, damping=0.99)
+        assert got.tobytes() == ref.tobytes(), (n, S, shape, n_active, fuse, chunk, seed)
+        assert info[2] == 1
+    check()
