@@ -266,7 +266,9 @@ def run_mapc(args) -> None:
 
     c = pkg.Compute(n, local_rank, rank=rank, world=world, nccl_id=nccl_id)
     c.Upload(particles)
-    if world > 1 and args.exchange == "peer":
+    if args.exchange == "peer-single":
+        os.environ["MAPC_PEER_SINGLE"] = "1"
+    if world > 1 and args.exchange.startswith("peer"):
         pkg.dist.enable_peer_exchange(c, dev)
     sh = c.GetSharedHandles()
     stream = torch.cuda.ExternalStream(sh.compute_stream, device=dev)
@@ -316,7 +318,7 @@ def run_mapc(args) -> None:
     host_out = torch.empty((c.num_local, 8), dtype=torch.float32, pin_memory=True)
     out_view = host_out.numpy().view(pkg.POSVELO_DTYPE).reshape(-1)
     e2e_steps = max(1, min(args.steps, 10))
-    peer = world > 1 and args.exchange == "peer"
+    peer = world > 1 and args.exchange.startswith("peer")
 
     for _ in range(2):
         if peer:
@@ -414,8 +416,9 @@ def main() -> None:
     ap.add_argument("--bodies", "--n", dest="n", type=int, default=None,
                     help="override the number of bodies (use --bodies under torchrun: its parser rejects --n as ambiguous)")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
-    ap.add_argument("--exchange", choices=["nccl", "peer"], default="nccl",
-                    help="multi-GPU position exchange: NCCL all-gather, or direct peer-memory reads in the force kernel")
+    ap.add_argument("--exchange", choices=["nccl", "peer", "peer-single"], default="nccl",
+                    help="multi-GPU position exchange: NCCL all-gather, direct peer-memory reads in the force kernel, "
+                         "or the latter as one grid per step (experimental, MAPC_PEER_SINGLE=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=1,
                     help="issue the timed steps in batches of this many (mapc_compute_simulate_steps); latency runs")

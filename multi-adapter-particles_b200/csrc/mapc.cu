@@ -391,6 +391,7 @@ struct Switches {
     bool timer_events;  // MAPC_TIMER_EVENTS=1: cudaEvent pairs instead of in-kernel stamps
     bool kernel_fence;  // MAPC_KERNEL_FENCE=0: fence signalled by a stream operation, not by the kernel
     bool peer;          // MAPC_PEER=0: attached peer exchange not used
+    bool peer_single;   // MAPC_PEER_SINGLE=1 (experimental): peer exchange as ONE grid, local cells first
     int plan_pairs, plan_threads;  // MAPC_PLAN_PAIRS / MAPC_PLAN_THREADS: force a launch shape (0 = choose)
 };
 
@@ -407,6 +408,7 @@ Switches read_switches()
     w.timer_events = env_int("MAPC_TIMER_EVENTS", 0) != 0;
     w.kernel_fence = env_int("MAPC_KERNEL_FENCE", 1) != 0;
     w.peer = env_int("MAPC_PEER", 1) != 0;
+    w.peer_single = env_int("MAPC_PEER_SINGLE", 0) != 0;
     w.plan_pairs = env_int("MAPC_PLAN_PAIRS", 0);
     w.plan_threads = env_int("MAPC_PLAN_THREADS", 0);
     return w;
@@ -1063,7 +1065,8 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             // waits for the all-gather, so both grids are resident together and the block scheduler
             // balances them (a lone local launch of few, long cells would leave most SMs idle).  The
             // arrival counters make the fused combine+integrate independent of which grid finishes last.
-            if (remote.count > 0) MAPC_CUDA(cudaEventRecord(c->ev_step_begin, c->compute));
+            const bool single_grid = use_peer && sw.peer_single && remote.count > 0;
+            if (remote.count > 0 && !single_grid) MAPC_CUDA(cudaEventRecord(c->ev_step_begin, c->compute));
             // MAPC_MASS_IN_LOOP=1: the shader's per-pair `mass * invDistCube` (12 lane-ops) instead of the
             // default once-per-partial scale (11): A/B switch, fused non-peer path only
             const bool inloop = fuse && sw.mass_in_loop;
@@ -1073,6 +1076,28 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
                 return fuse ? launch_force_shape<true>(c, pl, args, st, staging)
                             : launch_force_shape<false>(c, pl, args, st, staging);
             };
+            if (single_grid) {
+                // Experimental (MAPC_PEER_SINGLE=1): one grid for the whole step.  blockIdx.y walks the local
+                // segments first and the remote ones after them, and blocks are dispatched in that order, so
+                // the cells that wait for a peer's step flag only become resident once the local cells are
+                // under way -- instead of a second grid whose blocks may sit on SMs spinning from the start.
+                // Same cells, same arithmetic, same partials: the bits cannot change.
+                mapc::SegList all{0, {}};
+                for (int k = 0; k < local.count; ++k) {
+                    args.seg_src[all.count] = c->packed[r];
+                    args.seg_flag[all.count] = nullptr;
+                    all.ids[all.count++] = local.ids[k];
+                }
+                for (int k = 0; k < remote.count; ++k) {
+                    const int o = owner[remote.ids[k]];
+                    args.seg_src[all.count] = c->peer_packed[o][r];
+                    args.seg_flag[all.count] = c->peer_flag[o];
+                    all.ids[all.count++] = remote.ids[k];
+                }
+                args.flag_expect = c->step_id;
+                args.segs = all;
+                MAPC_TRY((launch_force_shape<true, true>(c, pl, args, c->compute, kStageDefault)));
+            } else {
             args.segs = local;
             MAPC_TRY(launch(c->compute));
             if (local.count > 0) args.stamp_begin = nullptr;
@@ -1094,6 +1119,7 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
                 }
                 MAPC_CUDA(cudaEventRecord(c->ev_remote_done, c->compute2));
                 MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_remote_done, 0));
+            }
             }
             if (!fuse) {
                 mapc::integrate_kernel<<<(n_targets + 255) / 256, 256, 0, c->compute>>>(

@@ -83,6 +83,7 @@ extern "C" {
 // that are not targets keep them).  pos_next_out: n float4, the packed mirror of the written side as rank 0
 // .. world-1 wrote it (own shards only).  info[0] = kernel launches, info[1] = fence word after the step,
 // info[2] = 1 if every arrival counter and the `done` counter were back at zero.
+// peer: 0 NCCL layout, 1 peer layout (local + remote launch), 2 peer layout as one grid (MAPC_PEER_SINGLE=1).
 // chunk: 0, or the CHUNK template value (sources per bounded chain: 256 or 2048).
 // staging: 0 LDG/STS + LDS broadcast (default), 1 TMA bulk copies (MAPC_TMA=1), 2 warp-shuffle broadcast (MAPC_SHFL=1).
 // returns 0, or -1 for an unknown shape / variant, -2 for a layout the library would refuse (peer with
@@ -152,6 +153,24 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
         const bool peer_ok = peer && fuse && n_sources == n && !mass_in_loop && chunk == 0 && lay.aligned;
         if (peer && world > 1 && !peer_ok && remote.count > 0) return -2;
 
+        if (peer == 2 && peer_ok && world > 1 && remote.count > 0) {
+            // MAPC_PEER_SINGLE=1 as csrc/mapc.cu builds it: one grid, local segments first, then the remote ones
+            mapc::SegList all{0, {}};
+            for (int k = 0; k < local.count; ++k) {
+                a.seg_src[all.count] = packed[r].data();
+                a.seg_flag[all.count] = nullptr;
+                all.ids[all.count++] = local.ids[k];
+            }
+            for (int k = 0; k < remote.count; ++k) {
+                a.seg_src[all.count] = packed[owner[remote.ids[k]]].data();
+                a.seg_flag[all.count] = &flags[owner[remote.ids[k]]];
+                all.ids[all.count++] = remote.ids[k];
+            }
+            a.flag_expect = 7;
+            a.segs = all;
+            if (!launch_force(pairs, threads, fuse, true, mass_in_loop, chunk, 0, a, block_order)) return -1;
+            ++launches;
+        } else {
         a.segs = local;
         if (!launch_force(pairs, threads, fuse, false, mass_in_loop, chunk, staging, a, block_order)) return -1;
         launches += (local.count > 0);
@@ -168,6 +187,7 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
             }
             if (!launch_force(pairs, threads, fuse, use_peer, mass_in_loop, chunk, use_peer ? 0 : staging, a, block_order)) return -1;
             ++launches;
+        }
         }
         if (!fuse) {
             // MAPC_FUSE=0: the separate combine + integrate, as csrc/mapc.cu launches it

@@ -23,7 +23,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bodies", dest="n", type=int, nargs="+", default=[8192, 10_000, 32_768, 262_144])
     ap.add_argument("--steps", type=int, default=4)
-    ap.add_argument("--exchange", choices=["nccl", "peer", "both"], default="both")
+    ap.add_argument("--exchange", choices=["nccl", "peer", "peer-single", "both", "all"], default="both",
+                    help="peer-single = the experimental one-grid peer exchange (MAPC_PEER_SINGLE=1); all = the three")
     args = ap.parse_args()
 
     import torch
@@ -35,7 +36,7 @@ def main():
     pkg = importlib.import_module("multi-adapter-particles_b200")
     pkg.load()
     ok = True
-    modes = ["nccl", "peer"] if args.exchange == "both" else [args.exchange]
+    modes = {"both": ["nccl", "peer"], "all": ["nccl", "peer", "peer-single"]}.get(args.exchange, [args.exchange])
     for n in args.n:
         if n % world:
             continue
@@ -53,14 +54,17 @@ def main():
             S = pkg.plan_segments(n)
             aligned = all((a // count) == ((b - 1) // count) for a, b in
                           (pkg.dist.segment_range(n, S, k) for k in range(S)) if b > a)
-            if mode == "peer" and not aligned:
+            os.environ.pop("MAPC_PEER_SINGLE", None)
+            if mode == "peer-single":
+                os.environ["MAPC_PEER_SINGLE"] = "1"
+            if mode.startswith("peer") and not aligned:
                 if rank == 0:
-                    print(f"n={n} world={world} exchange=peer skipped (segments straddle shards)", flush=True)
+                    print(f"n={n} world={world} exchange={mode} skipped (segments straddle shards)", flush=True)
                 continue
             nid = pkg.dist.broadcast_bytes(pkg.nccl_unique_id() if rank == 0 else None, pkg.NCCL_UNIQUE_ID_BYTES, 0, dev)
             with pkg.Compute(n, local_rank, rank=rank, world=world, nccl_id=nid) as c:
                 c.Upload(p)
-                if mode == "peer":
+                if mode.startswith("peer"):
                     pkg.dist.enable_peer_exchange(c, dev)
                 else:
                     dist.barrier()

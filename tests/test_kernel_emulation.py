@@ -389,3 +389,19 @@ def test_fuzz_sharded_layouts_against_oracle(emu, oracle, mapc):
         assert out.tobytes() == ref.tobytes(), (world, n, S, shape, peer, seed)
         assert mirror.tobytes() == ref["pos"].tobytes() and info[2] == 1
     check()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_single_grid_peer_exchange_bitwise(emu, oracle, mapc, world):
+    """MAPC_PEER_SINGLE=1 (experimental): the peer exchange as ONE grid whose segment list holds the local
+    segments first and the remote ones after them, every entry with its own source array and step flag (none
+    for the local ones).  Same cells and partials, so the same bits as two launches -- and as one GPU."""
+    n = 2048
+    p = mapc.ic.uniform_sphere(n, 400.0, seed=11, speed=1.0)
+    S = mapc.plan_segments(n)
+    ref = oracle_step(oracle, p, S)
+    for shape in ((4, 128), (1, 64)):
+        got, mirror, info = emu_step(emu, p, S, shape, world=world, peer=2)
+        assert got.tobytes() == ref.tobytes(), (shape, world)
+        assert mirror.tobytes() == ref["pos"].tobytes()
+        assert info[0] == world and info[2] == 1            # one launch per rank

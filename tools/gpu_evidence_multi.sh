@@ -27,10 +27,16 @@ run() {   # run <name> <bench args...>
 echo "=== multi-GPU tests" >&2
 timeout 1200 python -m pytest tests/test_multi_gpu.py -q -m gpu > "$OUT/${TAG}_pytest_multi_gpu.log" 2>&1
 tail -5 "$OUT/${TAG}_pytest_multi_gpu.log" >&2
+echo "=== bit-identity incl. the experimental one-grid peer exchange" >&2
+PORT=$((PORT + 1))
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$GPUS" --master-addr 127.0.0.1 \
+    --master-port "$PORT" tests/mgpu_worker.py --exchange all > "$OUT/${TAG}_mgpu_worker_all.log" 2>&1
+tail -15 "$OUT/${TAG}_mgpu_worker_all.log" >&2
 
 run "bench_${GPUS}gpu_config4_nccl" --bodies 1048576 --steps 10 --warmup 3 --exchange nccl
 run "bench_${GPUS}gpu_config4_peer" --bodies 1048576 --steps 10 --warmup 3 --exchange peer
 run "bench_${GPUS}gpu_weak_nccl" --steps 10 --warmup 3 --exchange nccl
 run "bench_${GPUS}gpu_weak_peer" --steps 10 --warmup 3 --exchange peer
+run "bench_${GPUS}gpu_weak_peer_single" --steps 10 --warmup 3 --exchange peer-single
 run "bench_${GPUS}gpu_strong_nccl" --scaling strong --steps 3 --warmup 3 --exchange nccl
 ls -la "$OUT" | grep "${TAG}_" >&2
