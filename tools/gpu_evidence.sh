@@ -9,6 +9,7 @@
 #   <tag>_bench_reference.json      bench.py --impl reference
 #   <tag>_bench_n10000*.json        config 2, single calls and batches of 50
 #   <tag>_bench_*_chunk.json        the same lines with MAPC_CHUNK=1 (bounded chains)
+#   <tag>_ubench_s32.txt            FP32-pipe microbenchmarks and the library's launch shapes at S = 32
 #   <tag>_launches.csv              ncu launch list of the bench command (gpu__time_duration.sum per launch)
 #   <tag>_force_full.ncu-rep/.csv   ncu --set full of one force kernel launch + its raw page as CSV
 #   <tag>_ncu_traffic.json          dram bytes per launch of that capture, in the format bench.py reads
@@ -43,6 +44,11 @@ timeout 600 python bench.py --bodies 4194304 --steps 2 --warmup 3 --no-cpu-basel
     > "$OUT/${TAG}_bench_n4194304.json" 2>> "$OUT/${TAG}_bench_n262144.err"
 MAPC_CHUNK=1 timeout 600 python bench.py --bodies 4194304 --steps 2 --warmup 3 --no-cpu-baseline \
     > "$OUT/${TAG}_bench_n4194304_chunk.json" 2>> "$OUT/${TAG}_bench_n262144.err"
+
+step "microbenchmarks + library shapes with the current S (tools/ubench N targets S)"
+if [ -x tools/ubench ]; then
+    timeout 600 tools/ubench 262144 0 32 > "$OUT/${TAG}_ubench_s32.txt" 2>&1
+fi
 
 step "ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
