@@ -35,6 +35,11 @@ constexpr int kChains = 8;
 // pattern 2: acc[k] = fma2(x[k], s, acc[k])    three pairs, s shared by neighbours
 // pattern 3: acc[k] = fma2(x[k], x[k], acc[k]) two distinct pairs
 // pattern 4: acc[k] = fma2(x[k], c[k].F32 broadcast, acc[k])  two pairs + one scalar
+// pattern 5: acc[k] = fma2(x[k], y[k], acc[k]); y[k] = fma2(y[k], y[k], 25)   a 3-pair op followed by a 1-pair op:
+//            does the operand fetch average over neighbouring instructions (2 reads/op -> ~2.06 cycles) or is it
+//            paid per instruction (3.06 + 2.06)/2?  (values run off to inf: irrelevant for the timing)
+// pattern 6: y[k] = fma2(y[k], y[k], 25)        one fetched pair, immediate addend (the 1-pair baseline)
+// pattern 7: acc[k] = fadd2(s.x broadcast, -x[k])   the subtraction r = bj - bi: one pair + one scalar
 template <int PATTERN>
 __global__ void __launch_bounds__(256) mb_ffma2(float2 *out, const float2 *__restrict__ in)
 {
@@ -55,11 +60,17 @@ __global__ void __launch_bounds__(256) mb_ffma2(float2 *out, const float2 *__res
             if (PATTERN == 2) acc[k] = __ffma2_rn(x[k], s, acc[k]);
             if (PATTERN == 3) acc[k] = __ffma2_rn(x[k], x[k], acc[k]);
             if (PATTERN == 4) acc[k] = __ffma2_rn(x[k], make_float2(y[k].x, y[k].x), acc[k]);
+            if (PATTERN == 5) {
+                acc[k] = __ffma2_rn(x[k], y[k], acc[k]);
+                y[k] = __ffma2_rn(y[k], y[k], make_float2(25.f, 25.f));
+            }
+            if (PATTERN == 6) y[k] = __ffma2_rn(y[k], y[k], make_float2(25.f, 25.f));
+            if (PATTERN == 7) acc[k] = __fadd2_rn(make_float2(s.x, s.x), make_float2(-acc[k].x, -acc[k].y));
         }
     }
     float2 r = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < kChains; ++k) r = __fadd2_rn(r, acc[k]);
+    for (int k = 0; k < kChains; ++k) r = __fadd2_rn(r, __fadd2_rn(acc[k], PATTERN >= 5 ? y[k] : make_float2(0.f, 0.f)));
     out[blockIdx.x * 256 + threadIdx.x] = r;
 }
 
@@ -235,6 +246,9 @@ int main(int argc, char **argv)
         report("FFMA2 acc=fma2(x[k],s,acc)      3 pairs, s shared (reuse)", t.best([&] { mb_ffma2<2><<<blocks, threads>>>(sink, input); }), per);
         report("FFMA2 acc=fma2(x[k],x[k],acc)   2 distinct pairs", t.best([&] { mb_ffma2<3><<<blocks, threads>>>(sink, input); }), per);
         report("FFMA2 acc=fma2(x[k],c[k].F32,acc) 2 pairs + scalar broadcast", t.best([&] { mb_ffma2<4><<<blocks, threads>>>(sink, input); }), per);
+        report("FFMA2 3-pair op then 1-pair op (does operand fetch average?)", t.best([&] { mb_ffma2<5><<<blocks, threads>>>(sink, input); }), 2.0 * per);
+        report("FFMA2 y=fma2(y,y,25)            1 fetched pair, immediate addend", t.best([&] { mb_ffma2<6><<<blocks, threads>>>(sink, input); }), per);
+        report("FADD2 acc=fadd2(s.F32,-acc)     1 pair + scalar broadcast (r = bj - bi)", t.best([&] { mb_ffma2<7><<<blocks, threads>>>(sink, input); }), per);
         report("FFMA  acc=fma(acc,a,b)          1 fetched reg", t.best([&] { mb_ffma<0><<<blocks, threads>>>(sink, input); }), per);
         report("FFMA  acc=fma(x[k],y[k],acc)    3 distinct regs (free allocation)", t.best([&] { mb_ffma<1><<<blocks, threads>>>(sink, input); }), per);
         report("FFMA  on halves of packed pairs  3 distinct regs, same parity", t.best([&] { mb_ffma<2><<<blocks, threads>>>(sink, input); }), per);
