@@ -169,7 +169,7 @@ struct Timer {
 static int g_sms = 148;
 static double g_peak_tflops = 74.45;
 
-static int g_segments = 8;  // canonical S (argv[3])
+static int g_segments = 32;  // canonical S (argv[3]); the library's rule gives 32 up to N = 262,144
 static int g_targets = 0;   // 0 = all bodies are targets; otherwise a shard of that many (multi-GPU shapes)
 
 template <int P, int T, int TJ, int U, int MINB, int ORDER = 0, bool TMA = false, bool INLOOP = false>
@@ -207,7 +207,8 @@ int main(int argc, char **argv)
 {
     const int n = argc > 1 ? atoi(argv[1]) : 262144;
     g_targets = argc > 2 ? atoi(argv[2]) : 0;
-    g_segments = argc > 3 ? atoi(argv[3]) : 8;
+    g_segments = argc > 3 ? atoi(argv[3]) : 32;
+    if (g_segments < 1 || g_segments > 64) { fprintf(stderr, "S must be in 1..64\n"); return 2; }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     g_sms = prop.multiProcessorCount;
@@ -275,7 +276,7 @@ int main(int argc, char **argv)
     CK(cudaMalloc(&pos, sizeof(float4) * n));
     CK(cudaMalloc(&partial, sizeof(float4) * n * 64));
     CK(cudaMemcpy(pos, h.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
-    printf("--- force_cells_kernel, %d sources, %d targets, S = 8 ---\n", n, g_targets > 0 ? g_targets : n);
+    printf("--- force_cells_kernel, %d sources, %d targets, S = %d ---\n", n, g_targets > 0 ? g_targets : n, g_segments);
 #ifdef SWEEP_SMALL
     run_force<1, 64, 64, 8, 16, 0>(pos, partial, n, t);
     run_force<1, 64, 64, 8, 18, 0>(pos, partial, n, t);
