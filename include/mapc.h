@@ -42,7 +42,10 @@ extern "C" {
 #define MAPC_PARTICLE_SPREAD        400.0f     /* Particles/defines.h:42                       */
 #define MAPC_MIN_NUM_PARTICLES      (256 * 1024)       /* Particles/defines.h:44               */
 #define MAPC_MAX_NUM_PARTICLES      (4 * 1024 * 1024)  /* Particles/defines.h:45               */
-#define MAPC_MAX_SEGMENTS           128
+/* Canonical summation order (frozen): S = 32 source segments for every N; inside a
+ * segment, sequential chains of at most 2,048 sources whose sums are folded left to right. */
+#define MAPC_MAX_SEGMENTS           32
+#define MAPC_CHAIN_SOURCES          2048
 #define MAPC_NCCL_UNIQUE_ID_BYTES   128
 #define MAPC_IPC_BLOB_BYTES         256
 
@@ -257,12 +260,16 @@ MAPC_API mapc_status mapc_consumer_counters(const mapc_consumer *r, uint64_t out
 MAPC_API mapc_status mapc_consumer_wait_for_gpu(mapc_consumer *r);
 
 /* ---- plan / diagnostics -------------------------------------------------------------------- */
-/* canonical number of j segments for n sources: 32 up to 262,144 sources, then 64 (up to 524,288) and
- * 128: each segment is one sequential fp32 accumulation chain, and chains of at most 8,192 terms keep
- * the rounding noise of the sum well inside the 1e-5 parity tolerance (with 32,768-term chains two
- * correctly rounded fp32 implementations already differ by 1.07e-5 at N = 262,144).  The partial sums of
- * the segments are combined left to right, independent of the GPU count. */
+/* Canonical number of j segments: 32 for every n (a multiple of every supported GPU count, so no segment
+ * straddles two shards).  A segment is evaluated as sequential fp32 chains of MAPC_CHAIN_SOURCES sources,
+ * counted from the segment's first source; each chain sum is folded left to right into the segment's
+ * partial, and the 32 partials left to right into the acceleration -- independent of the GPU count, the
+ * launch shape and the order in which cells run.  Bounded chains keep the rounding noise of the sum
+ * independent of N: between two correctly rounded fp32 evaluations of the formula the worst target differs
+ * by ~2e-6 at N = 262,144 ... 4,194,304, against 1.07e-5 with 32,768-term chains. */
 MAPC_API int mapc_plan_segments(uint32_t n_sources);
+/* sources per sequential accumulation chain of the canonical order (MAPC_CHAIN_SOURCES) */
+MAPC_API int mapc_plan_chain_sources(void);
 /* number of this library's kernels launched by the handle so far */
 MAPC_API uint64_t mapc_compute_kernel_launches(const mapc_compute *c);
 /* Launch geometry the next all-pairs step would use (pairs of bodies per thread, threads per

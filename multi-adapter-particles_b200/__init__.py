@@ -68,7 +68,7 @@ EXPORTED_SYMBOLS = (
     "mapc_consumer_create", "mapc_consumer_destroy", "mapc_consumer_draw", "mapc_consumer_latest",
     "mapc_consumer_wait_for_gpu", "mapc_consumer_counters",
     "mapc_compute_ipc_export", "mapc_compute_ipc_attach", "mapc_compute_simulate_steps",
-    "mapc_compute_exchange_times",
+    "mapc_compute_exchange_times", "mapc_plan_chain_sources",
 )
 
 
@@ -162,6 +162,7 @@ def load() -> ctypes.CDLL:
         "mapc_compute_ipc_attach": (c_int, [c_void_p, c_void_p, c_int]),
         "mapc_compute_simulate_steps": (c_int, [c_void_p, c_int, c_float, c_float, c_uint64, c_int]),
         "mapc_compute_exchange_times": (c_int, [c_void_p, P(c_float), P(c_float)]),
+        "mapc_plan_chain_sources": (c_int, []),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -185,6 +186,11 @@ def device_count() -> int:
 def plan_segments(n_sources: int) -> int:
     """Canonical number of j segments for ``n_sources`` sources (independent of the GPU count)."""
     return int(load().mapc_plan_segments(n_sources))
+
+
+def plan_chain_sources() -> int:
+    """Sources per sequential accumulation chain of the canonical order (MAPC_CHAIN_SOURCES)."""
+    return int(load().mapc_plan_chain_sources())
 
 
 def nccl_unique_id() -> bytes:

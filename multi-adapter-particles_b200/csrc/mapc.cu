@@ -385,7 +385,7 @@ struct Switches {
     bool pdl;           // MAPC_PDL=0: no programmatic dependent launch between consecutive steps
     bool tma;           // MAPC_TMA=1: cp.async.bulk source staging instead of LDG/STS
     bool shfl;          // MAPC_SHFL=1: warp-shuffle broadcast of staged sources instead of LDS broadcast
-    bool chunk;         // MAPC_CHUNK=1 (experimental, changes the bits): chains bounded at kChunkSources sources
+    bool ring;          // MAPC_RING=0: every target block its own scratch slot (no L2-resident ring)
     bool mass_in_loop;  // MAPC_MASS_IN_LOOP=1: 12-op pair with the shader's per-pair mass multiply
     bool timers;        // MAPC_TIMERS=0: no "simulate ms" timer at all
     bool timer_events;  // MAPC_TIMER_EVENTS=1: cudaEvent pairs instead of in-kernel stamps
@@ -402,7 +402,7 @@ Switches read_switches()
     w.pdl = env_int("MAPC_PDL", 1) != 0;
     w.tma = env_int("MAPC_TMA", 0) != 0;
     w.shfl = env_int("MAPC_SHFL", 0) != 0;
-    w.chunk = env_int("MAPC_CHUNK", 0) != 0;
+    w.ring = env_int("MAPC_RING", 1) != 0;
     w.mass_in_loop = env_int("MAPC_MASS_IN_LOOP", 0) != 0;
     w.timers = env_int("MAPC_TIMERS", 1) != 0;
     w.timer_events = env_int("MAPC_TIMER_EVENTS", 0) != 0;
@@ -441,8 +441,10 @@ struct mapc_compute {
     cudaEvent_t ev_step_begin = nullptr, ev_remote_done = nullptr;
     mapc_posvelo *posvelo[2] = {nullptr, nullptr};  // ping-pong sides, local shard
     float4 *packed[2] = {nullptr, nullptr};         // packed positions, all N, per side
-    float4 *partial = nullptr;                      // [segments][n_local]
-    int partial_segments = 0;
+    float4 *partial = nullptr;                      // partials scratch [slot][segment][block targets]
+    size_t partial_bytes = 0;
+    unsigned *slot_gen = nullptr;                   // scratch ring: target blocks combined out of each slot
+    int slot_gen_count = 0;
     mapc_posvelo *upload_stage = nullptr;           // sharded handles: landing buffer of Upload (all N)
     unsigned *counters = nullptr;                   // per target block: segments finished this step
     int counters_key = 0;                           // block size the counters were last used with
@@ -475,7 +477,7 @@ struct mapc_compute {
     bool t_stamped[kTimerSlots] = {};          // slot timed by in-kernel %globaltimer stamps, not events
     uint64_t t_fence_value[kTimerSlots] = {};  // fence value signalled after the slot's step(s)
     unsigned long long *stamps = nullptr;      // pinned host: [slot][begin, end] in ns
-    unsigned *done = nullptr;                  // device: target blocks integrated this step
+    unsigned *done = nullptr;                  // device: [0] target blocks integrated this step, [1] cell ticket
     unsigned long long *stamp_begin_next = nullptr, *stamp_end_next = nullptr;  // for the next force launch(es)
     unsigned long long fence_write_next = 0;   // != 0: the step's last block writes this value to the fence word
     uint64_t t_next = 0, t_resolved = 0;
@@ -525,13 +527,13 @@ void resolve_timers(mapc_compute *c, bool block)
     }
 }
 
-// grid = (target blocks, segments of this launch): one cell per thread block
+// grid = target blocks x segments of this launch, one cell per thread block, segment index fastest
 template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER, bool INLOOP, bool TMA,
-          bool SHFL = false, int CHUNK = 0>
+          bool SHFL = false>
 mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream_t stream)
 {
-    auto kernel = mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER, TMA, INLOOP, SHFL, CHUNK>;
-    dim3 grid((unsigned)args.n_iblocks, (unsigned)args.segs.count, 1);
+    auto kernel = mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER, TMA, INLOOP, SHFL>;
+    dim3 grid((unsigned)args.n_iblocks * (unsigned)args.segs.count, 1, 1);
     if (c->pdl_next) {
         // batched steps: the grid may be scheduled while the previous step's grid drains (the kernel
         // waits on griddepcontrol.wait before reading anything the previous step wrote)
@@ -560,10 +562,7 @@ mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream
 //                            of the 256-body-stage shapes: a wash, +0.7 % unfused in tools/ubench, -0.8 %
 //                            for the fused kernel (24.29 vs 24.09 ms at N = 262,144);
 //   kStageShfl  MAPC_SHFL=1  warp-shuffle broadcast of the staged bodies instead of the LDS broadcast.
-// A third alternative is NOT bit-identical (experimental, never the default):
-//   kStageChunk MAPC_CHUNK=1 chains bounded at kChunkSources sources: chunk sums folded into the partial.
-enum Staging { kStageDefault = 0, kStageTma = 1, kStageShfl = 2, kStageChunk = 3 };
-constexpr int kChunkSources = 2048;
+enum Staging { kStageDefault = 0, kStageTma = 1, kStageShfl = 2 };
 
 template <bool FUSE, bool PEER = false, bool INLOOP = false>
 mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::StepArgs &args, cudaStream_t stream,
@@ -573,14 +572,10 @@ mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::Step
     constexpr bool kAlt = FUSE && !PEER && !INLOOP;   // the alternatives are instantiated for this path only
     const bool tma = kAlt && staging == kStageTma;
     const bool shfl = kAlt && staging == kStageShfl;
-    if (staging == kStageChunk && !kAlt)
-        return fail(MAPC_ERR_UNSUPPORTED, "MAPC_CHUNK=1 exists for the fused, non-peer, mass-per-partial kernel only");
-    const bool chunk = kAlt && staging == kStageChunk;
 #define MAPC_SHAPE(P, T, TJ, U, MINB, ORDER, HAS_TMA)                                                          \
     if (pl.pairs == P && pl.threads == T) {                                                                   \
         if (HAS_TMA && tma) return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, kAlt && HAS_TMA>(c, args, stream); \
         if (shfl) return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false, kAlt>(c, args, stream); \
-        if (chunk) return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false, false, kAlt ? kChunkSources : 0>(c, args, stream); \
         return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false>(c, args, stream);             \
     }
     // unroll / order / blocks-per-SM per shape from the fused kernel measured in the library at N = 262,144
@@ -597,16 +592,29 @@ int local_targets(const mapc_compute *c, int n_active)
     return mapc::local_targets(c->n, c->i_first, c->n_local, n_active);
 }
 
-mapc_status ensure_partial(mapc_compute *c, int segments)
+// partials scratch and (for the ring) its per-slot release counters, grown on demand
+mapc_status ensure_partial(mapc_compute *c, const mapc::Scratch &sc)
 {
-    if (c->partial && c->partial_segments >= segments) return MAPC_OK;
-    if (c->partial) {
-        MAPC_CUDA(cudaStreamSynchronize(c->compute));
-        MAPC_CUDA(cudaFree(c->partial));
-        c->partial = nullptr;
+    if (!c->partial || c->partial_bytes < sc.bytes) {
+        if (c->partial) {
+            MAPC_CUDA(cudaStreamSynchronize(c->compute));
+            MAPC_CUDA(cudaStreamSynchronize(c->compute2));
+            MAPC_CUDA(cudaFree(c->partial));
+            c->partial = nullptr;
+        }
+        MAPC_CUDA(cudaMalloc(&c->partial, sc.bytes));
+        c->partial_bytes = sc.bytes;
     }
-    MAPC_CUDA(cudaMalloc(&c->partial, (size_t)segments * c->n_local * sizeof(float4)));
-    c->partial_segments = segments;
+    if (sc.ring && c->slot_gen_count < sc.slots) {
+        if (c->slot_gen) {
+            MAPC_CUDA(cudaStreamSynchronize(c->compute));
+            MAPC_CUDA(cudaFree(c->slot_gen));
+            c->slot_gen = nullptr;
+        }
+        MAPC_CUDA(cudaMalloc(&c->slot_gen, (size_t)sc.slots * sizeof(unsigned)));
+        MAPC_CUDA(cudaMemsetAsync(c->slot_gen, 0, (size_t)sc.slots * sizeof(unsigned), c->compute));
+        c->slot_gen_count = sc.slots;
+    }
     return MAPC_OK;
 }
 
@@ -658,7 +666,6 @@ mapc_status create_common(mapc_compute **out, uint32_t n, int device, int rank, 
             MAPC_CUDA(cudaEventCreate(&c->t_begin[k]));
             MAPC_CUDA(cudaEventCreate(&c->t_end[k]));
         }
-        MAPC_TRY(ensure_partial(c, mapc_plan_segments(n)));
         MAPC_CUDA(cudaHostAlloc((void **)&c->stamps, 2 * mapc_compute::kTimerSlots * sizeof(unsigned long long),
                                 cudaHostAllocPortable | cudaHostAllocMapped));
         memset(c->stamps, 0, 2 * mapc_compute::kTimerSlots * sizeof(unsigned long long));
@@ -708,20 +715,20 @@ mapc_status mapc_device_count(int *count)
     return MAPC_OK;
 }
 
-// Canonical segment count: a function of the number of sources only (never of the GPU count or the
-// launch shape).  Every segment is one sequential fp32 accumulation chain per target, so its length
-// sets the rounding noise of the sum: once a close neighbour has made the accumulator large, every later
-// term is rounded at that magnitude.  Measured at N = 262,144 over all targets, two correctly rounded CPU
-// evaluations of the same formula (oracle LITERAL vs MIRRORED) differ by 1.07e-5 with 32,768-term chains
-// (S = 8) -- the size of the parity tolerance itself -- and by 4.6e-6 with 8,192-term chains (S = 32).
-// So: 32 segments (also what small problems want for parallelism) while chains stay <= 8,192 terms,
-// then 64 and 128.
+// Canonical summation order (frozen): 32 segments for every N -- a multiple of every supported GPU count, so
+// no segment straddles two shards -- and, inside a segment, sequential fp32 chains of MAPC_CHAIN_SOURCES
+// sources whose sums are folded left to right into the segment's partial.  A chain's length sets the
+// rounding noise of the sum (once a close neighbour has made the accumulator large, every later term of the
+// chain is rounded at that magnitude): measured over all targets at N = 262,144, two correctly rounded CPU
+// evaluations of the same formula differ by 1.07e-5 with 32,768-term chains, 4.6e-6 with 8,192-term chains
+// and 2.5e-6 with these 2,048-term chains -- and by no more at N = 4,194,304.
 int mapc_plan_segments(uint32_t n_sources)
 {
-    int s = 32;
-    while (s < MAPC_MAX_SEGMENTS && (uint64_t)s * 8192u < n_sources) s *= 2;
-    return s;
+    (void)n_sources;
+    return MAPC_MAX_SEGMENTS;
 }
+
+int mapc_plan_chain_sources(void) { return MAPC_CHAIN_SOURCES; }
 
 // ---- fences ------------------------------------------------------------------------------------
 mapc_status mapc_fence_create(mapc_fence **out, uint64_t initial_value)
@@ -871,6 +878,7 @@ mapc_status mapc_compute_destroy(mapc_compute *c)
         if (c->ev_gather_begin[s]) cudaEventDestroy(c->ev_gather_begin[s]);
     }
     if (c->partial) cudaFree(c->partial);
+    if (c->slot_gen) cudaFree(c->slot_gen);
     if (c->counters) cudaFree(c->counters);
     if (c->done) cudaFree(c->done);
     if (c->stamps) cudaFreeHost(c->stamps);
@@ -1020,8 +1028,10 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             ++c->launches;
         } else {
             const Plan pl = make_plan(n_targets, n_sources, c->sm_count, sw);
-            MAPC_TRY(ensure_partial(c, pl.segments));
             const bool fuse = sw.fuse;
+            // scratch ring (stays in L2) for unsharded fused steps; everything else one slot per target block
+            const mapc::Scratch sc = mapc::plan_scratch(pl, c->sm_count, c->world == 1 && fuse && sw.ring);
+            MAPC_TRY(ensure_partial(c, sc));
             const int key = pl.pairs * 1024 + pl.threads;
             if (fuse && c->counters_key != key) {  // arrival counters are per target block of this shape
                 MAPC_CUDA(cudaMemsetAsync(c->counters, 0, ((size_t)c->n_local / 64 + 2) * sizeof(unsigned), c->compute));
@@ -1032,7 +1042,9 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             mapc::StepArgs args{};
             args.pos = c->packed[r];
             args.partial = c->partial;
-            args.partial_stride = (int)c->n_local;
+            args.scratch_blocks = sc.slots;
+            args.ticket = sc.ring ? c->done + 1 : nullptr;
+            args.slot_gen = sc.ring ? c->slot_gen : nullptr;
             args.i_first = (int)c->i_first;
             args.i_cnt = n_targets;
             args.n_sources = n_sources;
@@ -1054,7 +1066,7 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             const mapc::SegList &local = lay.local, &remote = lay.remote;
             const int *owner = lay.owner;
             const bool peer = c->peer_mode && fuse && n_sources == (int)c->n && sw.peer && !sw.mass_in_loop &&
-                              !sw.chunk && lay.aligned;
+                              lay.aligned;
             if (c->peer_mode && !peer && remote.count > 0 && !c->gather_pending[r]) {
                 // exchange falls back to NCCL for this step, but the read side was never gathered
                 return fail(MAPC_ERR_UNSUPPORTED, "peer exchange attached but this step's segments do not align "
@@ -1070,7 +1082,7 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             // MAPC_MASS_IN_LOOP=1: the shader's per-pair `mass * invDistCube` (12 lane-ops) instead of the
             // default once-per-partial scale (11): A/B switch, fused non-peer path only
             const bool inloop = fuse && sw.mass_in_loop;
-            const Staging staging = sw.chunk ? kStageChunk : (sw.shfl ? kStageShfl : (sw.tma ? kStageTma : kStageDefault));
+            const Staging staging = sw.shfl ? kStageShfl : (sw.tma ? kStageTma : kStageDefault);
             auto launch = [&](cudaStream_t st) -> mapc_status {
                 if (inloop) return launch_force_shape<true, false, true>(c, pl, args, st, staging);
                 return fuse ? launch_force_shape<true>(c, pl, args, st, staging)
@@ -1123,7 +1135,7 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             }
             if (!fuse) {
                 mapc::integrate_kernel<<<(n_targets + 255) / 256, 256, 0, c->compute>>>(
-                    c->posvelo[r], c->posvelo[b], c->packed[b], c->partial, (int)c->n_local, pl.segments,
+                    c->posvelo[r], c->posvelo[b], c->packed[b], c->partial, pl.block_targets(), pl.segments,
                     (int)c->i_first, n_targets, delta_time, damping);
                 MAPC_CUDA(cudaGetLastError());
                 ++c->launches;

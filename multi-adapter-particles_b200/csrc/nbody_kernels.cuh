@@ -12,10 +12,12 @@
 //    interactions and issue slots stop being the limit; the j body is a scalar-broadcast operand
 //    (SASS `R.F32`), so one LDS.128 per source body feeds 2*P interactions.
 //  * MUFU.RSQ (rsqrt.approx.ftz) replaces 1/sqrt: fxc lowers `1.0f/sqrt(x)` to `rsq` as well.
-//  * Sources are cut into S canonical segments (mapc_plan_segments); a block owns one
-//    (target block, segment) cell and writes one partial per target.  Partials are summed left
-//    to right by integrate_kernel, so the result does not depend on which launch / stream /
-//    GPU evaluated a segment, nor on P or the block size.
+//  * Canonical summation order (frozen): sources are cut into S = 32 segments
+//    (mapc_plan_segments), a segment into chains of MAPC_CHAIN_SOURCES = 2,048 sources; a chain is one
+//    sequential fp32 accumulation, the chain sums of a segment are folded left to right into the
+//    segment's partial (in shared memory), and the 32 partials left to right into the acceleration.
+//    A block owns one (target block, segment) cell and writes one partial per target, so the result
+//    does not depend on which launch / stream / GPU evaluated a segment, nor on P or the block size.
 //  * No tensor cores: the work is not a contraction (d^2 via a GEMM cancels catastrophically).
 #pragma once
 
@@ -165,8 +167,15 @@ __device__ __forceinline__ void integrate_body(const float4 pos_in, const float4
 // Everything one launch of the force kernel needs (passed by value).
 struct StepArgs {
     const float4 *pos;         // packed positions of the read side, global indexing (targets and sources)
-    float4 *partial;           // [S][partial_stride] float4, local target indexing
-    int partial_stride;
+    // partials scratch: [slot][S][T*2P] float4, slot = target block % scratch_blocks.  scratch_blocks ==
+    // n_iblocks: every target block has its own slot.  scratch_blocks < n_iblocks (unsharded fused steps):
+    // a small ring that stays in L2 -- a cell may overwrite a slot only after the target block that used it
+    // scratch_blocks blocks earlier has been combined (slot_gen), and cells are handed out through a ticket
+    // counter in (target block, segment) order, so every cell a block can wait for is already running.
+    float4 *partial;
+    int scratch_blocks;
+    unsigned *ticket;          // next cell of this launch, or null: cell = blockIdx.x
+    unsigned *slot_gen;        // [scratch_blocks] target blocks combined out of each slot this step, or null
     int i_first, i_cnt;        // local targets are bodies [i_first, i_first + i_cnt)
     int n_sources, S;          // canonical segmentation of the sources
     SegList segs;              // the segments this launch evaluates
@@ -189,7 +198,7 @@ struct StepArgs {
     // block that integrates the LAST target block of the step stamps it when it is done
     unsigned long long *stamp_begin;   // pinned host memory, or null
     unsigned long long *stamp_end;     // pinned host memory, or null
-    unsigned *done;                    // target blocks integrated so far this step (device)
+    unsigned *done;                    // target blocks integrated so far this step (device); never null for FUSE
     // fence signal from inside the kernel (ID3D12CommandQueue::Signal after the Dispatch, Compute.cpp:999):
     // the same last block stores fence_value to the fence word (pinned host memory) -- or null
     unsigned long long *fence_word;
@@ -238,6 +247,17 @@ __device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned lo
     return v;
 }
 
+__device__ __forceinline__ unsigned load_acquire_gpu(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void store_release_gpu(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // programmatic dependent launch (no-ops for a launch without the programmatic-serialization attribute)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -245,15 +265,23 @@ __device__ __forceinline__ void fence_mbarrier_init() { asm volatile("fence.mbar
 #endif  // !MAPC_HOST_EMULATION
 
 // Force kernel.  Work is cut into cells = (target block of T*2P bodies) x (canonical segment); one
-// thread block evaluates one cell: blockIdx.x = target block, blockIdx.y = index into args.segs.  (A
-// persistent variant that walked several cells per block was measured 25 % slower: with the targets
-// reloaded inside a loop ptxas re-pairs them with ~170 MOVs per 8 sources instead of keeping the
-// register pairs live.)  A thread owns 2P targets as P register pairs and streams the segment's
-// sources through shared memory in stages of TJ bodies (register prefetch of the next stage, one
-// barrier per stage); the math runs in 64-body tiles -- the reference tile (Particles/defines.h:37)
-// -- so only the globally last tile is ever ragged.
+// thread block evaluates one cell.  Cells are numbered target block major, segment fastest
+// (cell = ib * segs.count + k), so the S cells of a target block run next to each other in time and the
+// combine finds their partials in L2; the cell of a thread block is blockIdx.x, or -- a.ticket != null --
+// the next ticket of an atomic counter (then a cell with a smaller number is guaranteed to be running or
+// finished, which is what makes the scratch ring's wait deadlock-free without any assumption about the
+// order in which the hardware dispatches blocks).  (A persistent variant that walked several cells per
+// block was measured 25 % slower: with the targets reloaded inside a loop ptxas re-pairs them with ~170
+// MOVs per 8 sources instead of keeping the register pairs live.)  A thread owns 2P targets as P register
+// pairs and streams the segment's sources through shared memory in stages of TJ bodies (register prefetch
+// of the next stage, one barrier per stage); the math runs in 64-body tiles -- the reference tile
+// (Particles/defines.h:37) -- so only the globally last tile is ever ragged.
+// CHAIN: sources per sequential accumulation chain (MAPC_CHAIN_SOURCES in the product; the emulation tests
+// also instantiate 256 so that small problems have several chains per segment).  At the end of a chain the
+// chain sum -- scaled by the mass like the oracle's MIRRORED flavour -- is folded into the segment's partial,
+// which lives in shared memory (thread-private slots, no barrier): partial = c0, then partial += c1, ...
 // U = unroll of the source loop, MINB = resident blocks per SM asked of ptxas.  None of P, T, TJ, U,
-// MINB or ORDER changes a rounding: each target's chain is the same ops in ascending j.
+// MINB or ORDER changes a rounding: each target's chains are the same ops in ascending j.
 // PEER: the cell's sources are read straight from the owning GPU's memory (no all-gather): the block
 // first waits until the owner's step flag says its positions of this step are published.  Waiting
 // cannot deadlock: a peer's step k-1 never depends on this GPU's step k.
@@ -265,24 +293,20 @@ __device__ __forceinline__ void fence_mbarrier_init() { asm volatile("fence.mbar
 // uniform-address LDS.128 per source.  Same bodies in the same order, so bit-identical; measured
 // slower (profiles/), because the shared-memory broadcast read is already a single instruction per
 // source and the shuffles triple the non-FMA issue slots.  Off by default (MAPC_SHFL=1).
-// CHUNK > 0 (experimental, MAPC_CHUNK=1, off by default): the canonical order with bounded chains.  A
-// segment's sources are taken in chunks of CHUNK bodies (counted from the segment's first source); each
-// chunk is one sequential fp32 chain as before, and the chunk sums -- scaled by the mass like a partial --
-// are folded left to right into the segment's partial in global memory, ((c0 + c1) + c2) + ...  That
-// bounds the rounding noise of a chain independently of S and N at the price of one
-// 16-byte read-modify-write per target per CHUNK sources.  It changes the bits wherever a segment is
-// longer than CHUNK; the oracle's `chunk` parameter states the same order.
 template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER = false, bool TMA = false,
-          bool MASS_IN_LOOP = false, bool SHFL = false, int CHUNK = 0>
+          bool MASS_IN_LOOP = false, bool SHFL = false, int CHAIN = MAPC_CHAIN_SOURCES>
 __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_constant__ StepArgs a)
 {
     constexpr int kLoads = TJ / T;  // staging loads per thread per stage
     static_assert(TJ % T == 0 && TJ % MAPC_BLOCK_SIZE == 0, "stage must be a multiple of block and tile size");
-    static_assert(CHUNK % TJ == 0, "a chunk is a whole number of stages");
-    constexpr int kStagesPerChunk = CHUNK > 0 ? CHUNK / TJ : 1;
+    static_assert(CHAIN > 0 && CHAIN % TJ == 0, "a chain is a whole number of stages");
+    constexpr int kStagesPerChain = CHAIN / TJ;
+    constexpr int kBlockTargets = T * 2 * P;
     __shared__ __align__(128) float4 tile[2][TJ];
+    __shared__ float seg_acc[6 * P][T];   // the segment's partial while its chains are folded in: [3*q + axis][tid]
     __shared__ __align__(8) unsigned long long full_bar[2];
     __shared__ int s_is_last;
+    __shared__ unsigned s_cell;
 
     const int tid = threadIdx.x;
     if (TMA) {
@@ -294,16 +318,23 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
         __syncthreads();
     }
     const float4 *__restrict__ pos = a.pos;
-    const float4 *__restrict__ src = PEER ? a.seg_src[blockIdx.y] : a.pos;   // where this cell's sources live
     // Programmatic dependent launch (batched steps): let the next step's grid start filling SMs as this
     // one drains, and do not touch the previous step's output before that grid has completely finished.
     // Both are no-ops for a launch without the programmatic-serialization attribute.
     pdl_launch_dependents();
     pdl_wait();
-    if (FUSE && a.stamp_begin != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
-        *a.stamp_begin = global_timer_ns();
+    unsigned cell = blockIdx.x;
+    if (a.ticket != nullptr) {
+        if (tid == 0) s_cell = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        cell = s_cell;
+    }
+    const int ib = (int)(cell / (unsigned)a.segs.count);        // target block
+    const int kseg = (int)(cell - (unsigned)ib * (unsigned)a.segs.count);   // index into this launch's segment list
+    const float4 *__restrict__ src = PEER ? a.seg_src[kseg] : a.pos;   // where this cell's sources live
+    if (FUSE && a.stamp_begin != nullptr && cell == 0 && tid == 0) *a.stamp_begin = global_timer_ns();
     if (PEER) {
-        const unsigned long long *flag = a.seg_flag[blockIdx.y];
+        const unsigned long long *flag = a.seg_flag[kseg];
         if (flag != nullptr) {
             if (tid == 0)
                 while (load_acquire_sys(flag) < a.flag_expect) __nanosleep(200);
@@ -311,14 +342,13 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
         }
     }
     {
-        const int ib = blockIdx.x;
-        const int seg = a.segs.ids[blockIdx.y];
+        const int seg = a.segs.ids[kseg];
         int j0, j1;
         segment_range(a.n_sources, a.S, seg, j0, j1);
 
         // targets: thread owns local bodies i_block + q*T + tid, q = 0..2P-1 (coalesced in q);
         // pair p = (q = 2p, q = 2p+1).  Out-of-range lanes are clamped and never stored.
-        const int i_block = ib * (T * 2 * P);
+        const int i_block = ib * kBlockTargets;
         float2 nxi[P], nyi[P], nzi[P], ax[P], ay[P], az[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) {
@@ -335,7 +365,7 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
         }
 
         const int n_stages = (j1 - j0 + TJ - 1) / TJ;
-        int flushed = 0;  // CHUNK: chunk sums already folded into this cell's partial
+        int folded = 0;  // chains of this segment already folded into seg_acc
         float4 stage[kLoads];
         if (TMA) {
             if (n_stages > 0 && tid == 0) {
@@ -426,65 +456,65 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                 for (int l = 0; l < kLoads; ++l) tile[buf ^ 1][l * T + tid] = stage[l];
             }
             __syncthreads();
-            if (CHUNK > 0 && has_next && (t + 1) % kStagesPerChunk == 0) {
-                // end of a chunk with more sources to come: fold the chain into the partial, start a new one
-                float4 *part = a.partial + (size_t)seg * a.partial_stride;
+            if (has_next && (t + 1) % kStagesPerChain == 0) {
+                // end of a chain with more sources to come: fold the chain sum into the segment's partial
+                // (thread-private shared-memory slots) and start the next chain from zero
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    const int ia = i_block + (2 * p) * T + tid;
-                    const int ib2 = i_block + (2 * p + 1) * T + tid;
                     if (!MASS_IN_LOOP) {
                         const float2 m = make_float2(MAPC_PARTICLE_MASS, MAPC_PARTICLE_MASS);
                         ax[p] = __fmul2_rn(ax[p], m);
                         ay[p] = __fmul2_rn(ay[p], m);
                         az[p] = __fmul2_rn(az[p], m);
                     }
-                    if (ia < a.i_cnt) {
-                        float4 v = make_float4(ax[p].x, ay[p].x, az[p].x, 0.f);
-                        if (flushed > 0) {
-                            const float4 o = part[ia];
-                            v = make_float4(__fadd_rn(o.x, v.x), __fadd_rn(o.y, v.y), __fadd_rn(o.z, v.z), 0.f);
-                        }
-                        part[ia] = v;
-                    }
-                    if (ib2 < a.i_cnt) {
-                        float4 v = make_float4(ax[p].y, ay[p].y, az[p].y, 0.f);
-                        if (flushed > 0) {
-                            const float4 o = part[ib2];
-                            v = make_float4(__fadd_rn(o.x, v.x), __fadd_rn(o.y, v.y), __fadd_rn(o.z, v.z), 0.f);
-                        }
-                        part[ib2] = v;
+                    if (folded == 0) {
+                        seg_acc[6 * p + 0][tid] = ax[p].x;
+                        seg_acc[6 * p + 1][tid] = ay[p].x;
+                        seg_acc[6 * p + 2][tid] = az[p].x;
+                        seg_acc[6 * p + 3][tid] = ax[p].y;
+                        seg_acc[6 * p + 4][tid] = ay[p].y;
+                        seg_acc[6 * p + 5][tid] = az[p].y;
+                    } else {
+                        seg_acc[6 * p + 0][tid] = __fadd_rn(seg_acc[6 * p + 0][tid], ax[p].x);
+                        seg_acc[6 * p + 1][tid] = __fadd_rn(seg_acc[6 * p + 1][tid], ay[p].x);
+                        seg_acc[6 * p + 2][tid] = __fadd_rn(seg_acc[6 * p + 2][tid], az[p].x);
+                        seg_acc[6 * p + 3][tid] = __fadd_rn(seg_acc[6 * p + 3][tid], ax[p].y);
+                        seg_acc[6 * p + 4][tid] = __fadd_rn(seg_acc[6 * p + 4][tid], ay[p].y);
+                        seg_acc[6 * p + 5][tid] = __fadd_rn(seg_acc[6 * p + 5][tid], az[p].y);
                     }
                     ax[p] = ay[p] = az[p] = make_float2(0.f, 0.f);
                 }
-                ++flushed;
+                ++folded;
             }
         }
 
-        float4 *out = a.partial + (size_t)seg * a.partial_stride;
+        // the slot of the scratch this target block's partials go to; a ring slot must have been released
+        // by the target block that used it scratch_blocks blocks earlier (its combine has read everything)
+        const int slot = ib % a.scratch_blocks;
+        if (a.slot_gen != nullptr) {
+            if (tid == 0) {
+                const unsigned want = (unsigned)(ib / a.scratch_blocks);
+                while (load_acquire_gpu(a.slot_gen + slot) != want) __nanosleep(100);
+            }
+            __syncthreads();
+        }
+        float4 *out = a.partial + ((size_t)slot * a.S + seg) * kBlockTargets;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            const int ia = i_block + (2 * p) * T + tid;
-            const int ib2 = i_block + (2 * p + 1) * T + tid;
-            if (!MASS_IN_LOOP) {  // the uniform g_fParticleMass factor, once per (target, segment) partial
+            const int ra = (2 * p) * T + tid, rb = (2 * p + 1) * T + tid;   // row inside the target block
+            if (!MASS_IN_LOOP) {  // the uniform g_fParticleMass factor, once per chain sum
                 const float2 m = make_float2(MAPC_PARTICLE_MASS, MAPC_PARTICLE_MASS);
                 ax[p] = __fmul2_rn(ax[p], m);
                 ay[p] = __fmul2_rn(ay[p], m);
                 az[p] = __fmul2_rn(az[p], m);
             }
-            if (CHUNK > 0 && flushed > 0) {  // the last chunk joins the earlier ones
-                if (ia < a.i_cnt) {
-                    const float4 o = out[ia];
-                    out[ia] = make_float4(__fadd_rn(o.x, ax[p].x), __fadd_rn(o.y, ay[p].x), __fadd_rn(o.z, az[p].x), 0.f);
-                }
-                if (ib2 < a.i_cnt) {
-                    const float4 o = out[ib2];
-                    out[ib2] = make_float4(__fadd_rn(o.x, ax[p].y), __fadd_rn(o.y, ay[p].y), __fadd_rn(o.z, az[p].y), 0.f);
-                }
-                continue;
+            if (folded > 0) {  // the last chain joins the earlier ones
+                ax[p] = make_float2(__fadd_rn(seg_acc[6 * p + 0][tid], ax[p].x), __fadd_rn(seg_acc[6 * p + 3][tid], ax[p].y));
+                ay[p] = make_float2(__fadd_rn(seg_acc[6 * p + 1][tid], ay[p].x), __fadd_rn(seg_acc[6 * p + 4][tid], ay[p].y));
+                az[p] = make_float2(__fadd_rn(seg_acc[6 * p + 2][tid], az[p].x), __fadd_rn(seg_acc[6 * p + 5][tid], az[p].y));
             }
-            if (ia < a.i_cnt) out[ia] = make_float4(ax[p].x, ay[p].x, az[p].x, 0.f);
-            if (ib2 < a.i_cnt) out[ib2] = make_float4(ax[p].y, ay[p].y, az[p].y, 0.f);
+            if (i_block + ra < a.i_cnt) out[ra] = make_float4(ax[p].x, ay[p].x, az[p].x, 0.f);
+            if (i_block + rb < a.i_cnt) out[rb] = make_float4(ax[p].y, ay[p].y, az[p].y, 0.f);
         }
 
         if (FUSE) {
@@ -495,34 +525,47 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
             __syncthreads();
             if (s_is_last) {
                 __threadfence();
+                const float4 *part = a.partial + (size_t)slot * a.S * kBlockTargets;
 #pragma unroll
                 for (int q = 0; q < 2 * P; ++q) {
-                    const int i = i_block + q * T + tid;
+                    const int row = q * T + tid;
+                    const int i = i_block + row;
                     if (i < a.i_cnt) {
                         float sx = 0.f, sy = 0.f, sz = 0.f;
                         for (int s = 0; s < a.S; ++s) {
-                            const float4 pp = __ldcg(a.partial + (size_t)s * a.partial_stride + i);
+                            const float4 pp = __ldcg(part + (size_t)s * kBlockTargets + row);
                             sx = __fadd_rn(sx, pp.x);
                             sy = __fadd_rn(sy, pp.y);
                             sz = __fadd_rn(sz, pp.z);
                         }
-                        const float4 *src = reinterpret_cast<const float4 *>(a.in + i);
+                        const float4 *srcpv = reinterpret_cast<const float4 *>(a.in + i);
                         float4 pos_out, vel_out;
-                        integrate_body(src[0], src[1], sx, sy, sz, a.dt, a.damping, pos_out, vel_out);
+                        integrate_body(srcpv[0], srcpv[1], sx, sy, sz, a.dt, a.damping, pos_out, vel_out);
                         float4 *dst = reinterpret_cast<float4 *>(a.out + i);
                         dst[0] = pos_out;
                         dst[1] = vel_out;
                         a.pos_next[a.i_first + i] = pos_out;
                     }
                 }
-                if (tid == 0) a.counters[ib] = 0u;  // ready for the next step
-                if (a.stamp_end != nullptr) {
-                    __syncthreads();                 // every thread's integrate stores are issued
-                    if (tid == 0 && atomicAdd(a.done, 1u) + 1u == (unsigned)a.n_iblocks) {
-                        *a.done = 0u;                // the step is complete: this was its last target block
+                // Every thread's integrate stores are ordered before the counters below by its own fence and
+                // the barrier: whoever sees `done` complete (and then the fence word) sees the whole step.
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) {
+                    a.counters[ib] = 0u;  // ready for the next step
+                    if (a.slot_gen != nullptr) store_release_gpu(a.slot_gen + slot, (unsigned)(ib / a.scratch_blocks) + 1u);
+                    if (atomicAdd(a.done, 1u) + 1u == (unsigned)a.n_iblocks) {
+                        // the step is complete: this was its last target block.  Re-arm the step's counters.
                         __threadfence();
-                        *a.stamp_end = global_timer_ns();
-                        __threadfence_system();
+                        *a.done = 0u;
+                        if (a.ticket != nullptr) *a.ticket = 0u;
+                        if (a.slot_gen != nullptr)
+                            for (int s = 0; s < a.scratch_blocks; ++s) a.slot_gen[s] = 0u;
+                        __threadfence();
+                        if (a.stamp_end != nullptr) {
+                            *a.stamp_end = global_timer_ns();
+                            __threadfence_system();
+                        }
                         if (a.fence_word != nullptr) {
                             *reinterpret_cast<volatile unsigned long long *>(a.fence_word) = a.fence_value;
                             __threadfence_system();
@@ -537,16 +580,18 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
 // Sum the S segment partials left to right, integrate, write side b and the packed mirror.
 //   in/out       local PosVelo sides (index 0 = body i_first)
 //   pos_next     packed float4 positions of the side being written, global indexing
+//   partial      [target block][S][block_targets] (every target block its own slot: the unfused path has no ring)
 __global__ void __launch_bounds__(256)
 integrate_kernel(const mapc_posvelo *__restrict__ in, mapc_posvelo *__restrict__ out,
                  float4 *__restrict__ pos_next, const float4 *__restrict__ partial,
-                 int partial_stride, int S, int i_first, int n_targets, float dt, float damping)
+                 int block_targets, int S, int i_first, int n_targets, float dt, float damping)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_targets) return;
+    const int ib = i / block_targets, row = i - ib * block_targets;
     float ax = 0.f, ay = 0.f, az = 0.f;
     for (int s = 0; s < S; ++s) {
-        const float4 p = partial[(size_t)s * partial_stride + i];
+        const float4 p = partial[((size_t)ib * S + s) * block_targets + row];
         ax = __fadd_rn(ax, p.x);
         ay = __fadd_rn(ay, p.y);
         az = __fadd_rn(az, p.z);

@@ -17,6 +17,8 @@ struct Plan {
     int threads;  // T
     int blocks_x; // target blocks of T*2P bodies
     int segments; // canonical S
+    int minb;     // resident blocks per SM the shape is compiled for (csrc/force_shapes.inc)
+    int block_targets() const { return threads * 2 * pairs; }
 };
 
 // Launch shapes (P, T) with the FMA-pipe efficiency each reaches at large N (tools/ubench,
@@ -24,14 +26,14 @@ struct Plan {
 // at small N what decides is how evenly the cells fall on the 4 x SMs warp schedulers and how many
 // target lanes the last block leaves idle.  The shape changes neither the arithmetic nor its order
 // (only S does), so it is free to vary with N, the shard size and the device.
-struct Shape { int pairs, threads; float efficiency; };
-constexpr Shape kShapes[6] = {{4, 256, 0.763f}, {4, 128, 0.753f}, {2, 128, 0.754f},
-                              {2, 64, 0.734f},  {1, 64, 0.728f},  {1, 32, 0.722f}};
+struct Shape { int pairs, threads, minb; float efficiency; };
+constexpr Shape kShapes[6] = {{4, 256, 2, 0.763f}, {4, 128, 4, 0.753f}, {2, 128, 8, 0.754f},
+                              {2, 64, 8, 0.734f},  {1, 64, 16, 0.728f}, {1, 32, 32, 0.722f}};
 
 // S = mapc_plan_segments(n_sources); force_pairs / force_threads != 0 pin the shape (MAPC_PLAN_PAIRS / _THREADS)
 inline Plan make_plan(int n_targets, int S, int sm_count, int force_pairs, int force_threads)
 {
-    Plan best{1, 32, 0, S};
+    Plan best{1, 32, 0, S, 32};
     float best_score = -1.f;
     for (const Shape &sh : kShapes) {
         if ((force_pairs && force_pairs != sh.pairs) || (force_threads && force_threads != sh.threads)) continue;
@@ -46,7 +48,7 @@ inline Plan make_plan(int n_targets, int S, int sm_count, int force_pairs, int f
         const float score = (float)(sh.efficiency * used * std::min(bal_block, bal_warp));
         if (score > best_score) {
             best_score = score;
-            best = Plan{sh.pairs, sh.threads, bx, S};
+            best = Plan{sh.pairs, sh.threads, bx, S, sh.minb};
         }
     }
     return best;
@@ -63,6 +65,30 @@ inline int local_targets(uint32_t n, uint32_t i_first, uint32_t n_local, int n_a
     if (loc < 0) loc = 0;
     if (loc > (long long)n_local) loc = n_local;
     return (int)loc;
+}
+
+// Partials scratch of one step: [slot][S][block targets] float4.  Every target block gets its own slot
+// (slots == blocks_x), except for an unsharded fused step whose scratch would not fit the ring budget: then
+// `slots` < blocks_x slots are reused round-robin while they are still in L2 (force_cells_kernel: ticket +
+// slot_gen).  The ring holds at least twice the target blocks that can be in flight at once, so the
+// release wait practically never spins; correctness does not depend on that.
+struct Scratch {
+    int slots;
+    bool ring;
+    size_t bytes;
+};
+constexpr size_t kScratchRingBytes = 32u << 20;   // a quarter of the 126 MB L2
+
+inline Scratch plan_scratch(const Plan &pl, int sm_count, bool allow_ring)
+{
+    const size_t per_block = (size_t)pl.segments * pl.block_targets() * 16u;
+    Scratch sc{pl.blocks_x, false, per_block * (size_t)pl.blocks_x};
+    if (!allow_ring) return sc;
+    const int in_flight = (sm_count * 2 * pl.minb + pl.segments - 1) / pl.segments + 2;
+    const int by_budget = (int)(kScratchRingBytes / per_block);
+    const int slots = std::max(in_flight, by_budget);
+    if (slots < pl.blocks_x) sc = Scratch{slots, true, per_block * (size_t)slots};
+    return sc;
 }
 
 // Which canonical segments a rank can evaluate straight away and which must wait for the exchange.

@@ -32,10 +32,11 @@ int mapo_num_tiles(int n) { return (n + MAPO_TILE - 1) / MAPO_TILE; }
 
 int mapo_default_segments(int n)
 {
-    int s = 32;
-    while (s < 128 && (long long)s * 8192 < n) s *= 2;   /* chains of at most 8,192 terms while s < 128 */
-    return s;
+    (void)n;
+    return MAPO_SEGMENTS;
 }
+
+int mapo_default_chain(void) { return MAPO_CHAIN_SOURCES; }
 
 void mapo_segment_range(int n_sources, int S, int s, int *j0, int *j1)
 {
@@ -95,7 +96,7 @@ void mapo_body_body_interaction_mirrored(float ai[3], const float bj[4], const f
     ai[2] = fmaf(dz, inv3, ai[2]);
 }
 
-void mapo_accel_allpairs_scalar(const mapo_posvelo *in, int n_sources, int S, int flavour,
+void mapo_accel_allpairs_scalar(const mapo_posvelo *in, int n_sources, int S, int chain, int flavour,
                                 const int *targets, int n_targets, float *accel3)
 {
     for (int k = 0; k < n_targets; ++k) {
@@ -104,15 +105,23 @@ void mapo_accel_allpairs_scalar(const mapo_posvelo *in, int n_sources, int S, in
         for (int s = 0; s < S; ++s) {
             int j0, j1;
             mapo_segment_range(n_sources, S, s, &j0, &j1);
-            float p[3] = {0.f, 0.f, 0.f};
-            for (int j = j0; j < j1; ++j) {
-                if (flavour == MAPO_LITERAL)
-                    mapo_body_body_interaction(p, in[j].pos, in[i].pos, MAPO_PARTICLE_MASS, 1);
-                else
-                    mapo_body_body_interaction_mirrored(p, in[j].pos, in[i].pos, MAPO_PARTICLE_MASS);
-            }
-            if (flavour != MAPO_LITERAL) {                    /* once per (target, segment) partial */
-                p[0] *= MAPO_PARTICLE_MASS; p[1] *= MAPO_PARTICLE_MASS; p[2] *= MAPO_PARTICLE_MASS;
+            float p[3] = {0.f, 0.f, 0.f};                     /* the segment's partial */
+            const int step = (chain > 0 && j1 - j0 > chain) ? chain : (j1 - j0 > 0 ? j1 - j0 : 1);
+            for (int c0 = j0; c0 < j1 || c0 == j0; c0 += step) {
+                const int c1 = (c0 + step < j1) ? c0 + step : j1;
+                float c[3] = {0.f, 0.f, 0.f};                 /* one chain */
+                for (int j = c0; j < c1; ++j) {
+                    if (flavour == MAPO_LITERAL)
+                        mapo_body_body_interaction(c, in[j].pos, in[i].pos, MAPO_PARTICLE_MASS, 1);
+                    else
+                        mapo_body_body_interaction_mirrored(c, in[j].pos, in[i].pos, MAPO_PARTICLE_MASS);
+                }
+                if (flavour != MAPO_LITERAL) {                /* once per chain sum */
+                    c[0] *= MAPO_PARTICLE_MASS; c[1] *= MAPO_PARTICLE_MASS; c[2] *= MAPO_PARTICLE_MASS;
+                }
+                if (c0 == j0) { p[0] = c[0]; p[1] = c[1]; p[2] = c[2]; }
+                else { p[0] += c[0]; p[1] += c[1]; p[2] += c[2]; }
+                if (c1 >= j1) break;
             }
             total[0] += p[0];
             total[1] += p[1];
@@ -185,14 +194,14 @@ static void segment_block_mirrored(const mapo_posvelo *in, int j0, int j1,
 void mapo_accel_allpairs(const mapo_posvelo *in, int n_sources, int S, int flavour,
                          const int *targets, int n_targets, float *accel3, int threads)
 {
-    mapo_accel_allpairs_chunked(in, n_sources, S, 0, flavour, targets, n_targets, accel3, threads);
+    mapo_accel_allpairs_chunked(in, n_sources, S, MAPO_CHAIN_SOURCES, flavour, targets, n_targets, accel3, threads);
 }
 
-/* chunk > 0: the canonical order with bounded chains (csrc/nbody_kernels.cuh, template flag CHUNK): a
- * segment longer than `chunk` sources is evaluated as consecutive chunks of `chunk` sources counted from
- * the segment's first source; every chunk is one sequential chain (scaled by the mass like a partial in
- * the MIRRORED flavour) and the chunk sums are folded left to right, ((c0 + c1) + c2) + ..., into the
- * segment's partial.  chunk == 0: one chain per segment. */
+/* The canonical order (csrc/nbody_kernels.cuh, template parameter CHAIN): a segment longer than `chunk`
+ * sources is evaluated as consecutive chains of `chunk` sources counted from the segment's first source;
+ * every chain is one sequential accumulation (scaled by the mass once, in the MIRRORED flavour) and the
+ * chain sums are folded left to right, ((c0 + c1) + c2) + ..., into the segment's partial.  chunk == 0: one
+ * chain per segment (not what the product does; kept to show what bounded chains buy). */
 void mapo_accel_allpairs_chunked(const mapo_posvelo *in, int n_sources, int S, int chunk, int flavour,
                                  const int *targets, int n_targets, float *accel3, int threads)
 {
@@ -302,8 +311,8 @@ void mapo_step_allpairs_targets(const mapo_posvelo *in, int n_sources,
                                 const int *targets, int n_targets, float dt, float damping,
                                 int S, int flavour, int threads, mapo_posvelo *out_targets)
 {
-    mapo_step_allpairs_targets_chunked(in, n_sources, targets, n_targets, dt, damping, S, 0, flavour, threads,
-                                       out_targets);
+    mapo_step_allpairs_targets_chunked(in, n_sources, targets, n_targets, dt, damping, S, MAPO_CHAIN_SOURCES, flavour,
+                                       threads, out_targets);
 }
 
 void mapo_step_allpairs_targets_chunked(const mapo_posvelo *in, int n_sources,

@@ -29,10 +29,12 @@
  *   Particles/Compute.cpp:1041            Dispatch(ceil(nActive/64)) -> which bodies are updated
  *   Particles/defines.h:37                BLOCK_SIZE 64 (j tile)
  *
- * Summation shape (a build decision; the reference pins only "ascending j, tiles of 64"):
- * the sources j in [0, n_sources) are cut into S contiguous, tile-aligned segments;
- * inside a segment one fp32 accumulator per axis runs over ascending j; the S partials
- * are then added left to right, ((p0 + p1) + p2) + ... + p(S-1).
+ * Canonical summation order (a build decision, frozen; the reference pins only "ascending j, tiles of
+ * 64"): the sources j in [0, n_sources) are cut into S = 32 contiguous, tile-aligned segments; a segment
+ * is taken as consecutive chains of MAPO_CHAIN_SOURCES = 2,048 sources counted from its first source
+ * (the last one shorter); inside a chain one fp32 accumulator per axis runs over ascending j; the chain
+ * sums of a segment are folded left to right into the segment's partial, (c0 + c1) + c2 ..., and the S
+ * partials left to right into the acceleration, ((p0 + p1) + p2) + ... + p(S-1).
  */
 #ifndef MAPO_ORACLE_H
 #define MAPO_ORACLE_H
@@ -46,14 +48,16 @@ typedef struct { float pos[4]; float velo[4]; } mapo_posvelo; /* ParticleShared.
 #define MAPO_SOFTENING_SQUARED 25.0f   /* nBodyGravityCS.hlsl:37 */
 #define MAPO_PARTICLE_MASS     70000.0f /* nBodyGravityCS.hlsl:38 */
 #define MAPO_TILE              64      /* defines.h:37 */
+#define MAPO_SEGMENTS          32      /* canonical segment count, every N */
+#define MAPO_CHAIN_SOURCES     2048    /* canonical chain length */
 
 enum { MAPO_LITERAL = 0, MAPO_MIRRORED = 1 };
 
 /* dimx of Compute.cpp:544 */
 int  mapo_num_tiles(int n);
-/* canonical segment count for n sources: 32, doubling (up to 128) so that no segment exceeds 8,192
- * sources: bounds the rounding noise of the sequential fp32 chains (see mapc_plan_segments) */
+/* canonical segment count (32 for every n) and chain length (2,048 sources): see mapc_plan_segments */
 int  mapo_default_segments(int n);
+int  mapo_default_chain(void);
 /* j range [j0, j1) of segment s out of S over n_sources sources */
 void mapo_segment_range(int n_sources, int S, int s, int *j0, int *j1);
 /* number of bodies one Simulate(n_active) updates: min(n, 64*ceil(n_active/64)) (Compute.cpp:1041) */
@@ -68,17 +72,16 @@ void mapo_body_body_interaction(float ai[3], const float bj[4], const float bi[4
 void mapo_body_body_interaction_mirrored(float ai[3], const float bj[4], const float bi[4],
                                          float mass);
 
-/* accel of the listed targets (NULL = targets 0..n_targets-1) from sources [0, n_sources),
- * canonical S-segment order, one scalar call of the pair function per (i, j). Slow; small N. */
-void mapo_accel_allpairs_scalar(const mapo_posvelo *in, int n_sources, int S, int flavour,
+/* accel of the listed targets (NULL = targets 0..n_targets-1) from sources [0, n_sources), S segments,
+ * chains of `chain` sources (0 = one chain per segment), one scalar call of the pair function per (i, j).
+ * Slow; small N. */
+void mapo_accel_allpairs_scalar(const mapo_posvelo *in, int n_sources, int S, int chain, int flavour,
                                 const int *targets, int n_targets, float *accel3);
-/* same numbers (bit-identical), 8 targets per inner loop so gcc can vectorise across i;
- * OpenMP over target blocks; threads <= 0 means omp_get_max_threads(). */
+/* same numbers (bit-identical) with the canonical chain length, 8 targets per inner loop so gcc can
+ * vectorise across i; OpenMP over target blocks; threads <= 0 means omp_get_max_threads(). */
 void mapo_accel_allpairs(const mapo_posvelo *in, int n_sources, int S, int flavour,
                          const int *targets, int n_targets, float *accel3, int threads);
-/* the same with chains bounded at `chunk` sources (0 = one chain per segment): a longer segment is taken as
- * consecutive chunks counted from its first source, each one sequential chain, folded left to right into
- * the segment's partial -- the order of the kernels' experimental CHUNK variant (MAPC_CHUNK=1) */
+/* the same with chains of `chunk` sources instead of MAPO_CHAIN_SOURCES (0 = one chain per segment) */
 void mapo_accel_allpairs_chunked(const mapo_posvelo *in, int n_sources, int S, int chunk, int flavour,
                                  const int *targets, int n_targets, float *accel3, int threads);
 /* fp64 direct sum, ascending j, no segments -- reported alongside, never gating */

@@ -53,7 +53,9 @@ def load() -> ctypes.CDLL:
     lib.mapo_body_body_interaction_mirrored.restype = None
     lib.mapo_body_body_interaction_mirrored.argtypes = [fp, fp, fp, c_float]
     lib.mapo_accel_allpairs_scalar.restype = None
-    lib.mapo_accel_allpairs_scalar.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
+    lib.mapo_accel_allpairs_scalar.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
+    lib.mapo_default_chain.restype = c_int
+    lib.mapo_default_chain.argtypes = []
     lib.mapo_accel_allpairs.restype = None
     lib.mapo_accel_allpairs.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int]
     lib.mapo_accel_allpairs_chunked.restype = None
@@ -97,6 +99,16 @@ def default_segments(n: int) -> int:
     return int(load().mapo_default_segments(n))
 
 
+def default_chain() -> int:
+    """Sources per sequential accumulation chain of the canonical order (2,048)."""
+    return int(load().mapo_default_chain())
+
+
+def _chain(chunk) -> int:
+    """chunk=None: the canonical chain length; 0: one chain per segment (not what the product does)."""
+    return default_chain() if chunk is None else int(chunk)
+
+
 def num_targets(n: int, n_active: int) -> int:
     return int(load().mapo_num_targets(n, n_active))
 
@@ -127,7 +139,7 @@ def body_body_interaction(ai, bj, bi, mass=70000.0, particles=1, flavour=LITERAL
 
 
 def accel_allpairs(particles, n_sources=None, S=None, flavour=LITERAL, targets=None, threads=0,
-                   scalar=False, chunk=0) -> np.ndarray:
+                   scalar=False, chunk=None) -> np.ndarray:
     p = _pv(particles)
     n_sources = p.shape[0] if n_sources is None else n_sources
     S = default_segments(n_sources) if S is None else S
@@ -138,12 +150,9 @@ def accel_allpairs(particles, n_sources=None, S=None, flavour=LITERAL, targets=N
         nt, tp = t.shape[0], _ptr(t)
     out = np.zeros((nt, 3), dtype=np.float32)
     if scalar:
-        assert chunk == 0
-        load().mapo_accel_allpairs_scalar(_ptr(p), n_sources, S, flavour, tp, nt, _ptr(out))
-    elif chunk:
-        load().mapo_accel_allpairs_chunked(_ptr(p), n_sources, S, chunk, flavour, tp, nt, _ptr(out), threads)
+        load().mapo_accel_allpairs_scalar(_ptr(p), n_sources, S, _chain(chunk), flavour, tp, nt, _ptr(out))
     else:
-        load().mapo_accel_allpairs(_ptr(p), n_sources, S, flavour, tp, nt, _ptr(out), threads)
+        load().mapo_accel_allpairs_chunked(_ptr(p), n_sources, S, _chain(chunk), flavour, tp, nt, _ptr(out), threads)
     return out
 
 
@@ -161,38 +170,31 @@ def accel_fp64(particles, n_sources=None, targets=None, threads=0) -> np.ndarray
 
 
 def step_allpairs(particles, n_active=None, dt=0.1, damping=1.0, S=None, flavour=LITERAL, threads=0,
-                  out=None, chunk=0) -> np.ndarray:
-    """One all-pairs step.  `out` (the side being overwritten) defaults to a copy of the input.
-    chunk > 0: chains bounded at `chunk` sources (the kernels' experimental CHUNK order)."""
+                  out=None, chunk=None) -> np.ndarray:
+    """One all-pairs step in the canonical order.  `out` (the side being overwritten) defaults to a copy of
+    the input.  chunk: chain length (None = canonical 2,048; 0 = one chain per segment)."""
     p = _pv(particles)
     n = p.shape[0]
     n_active = n if n_active is None else n_active
     S = default_segments(min(n_active, n)) if S is None else S
     o = p.copy() if out is None else out
-    if chunk:
-        nt = num_targets(n, n_active)
-        new = np.zeros(nt, dtype=POSVELO_DTYPE)
-        load().mapo_step_allpairs_targets_chunked(_ptr(p), min(n_active, n), None, nt, dt, damping, S, chunk,
-                                                  flavour, threads, _ptr(new))
-        o[:nt] = new
-        return o
-    load().mapo_step_allpairs(_ptr(p), _ptr(o), n, n_active, dt, damping, S, flavour, threads)
+    nt = num_targets(n, n_active)
+    new = np.zeros(nt, dtype=POSVELO_DTYPE)
+    load().mapo_step_allpairs_targets_chunked(_ptr(p), min(n_active, n), None, nt, dt, damping, S, _chain(chunk),
+                                              flavour, threads, _ptr(new))
+    o[:nt] = new
     return o
 
 
 def step_allpairs_targets(particles, targets, n_sources=None, dt=0.1, damping=1.0, S=None, flavour=LITERAL,
-                          threads=0, chunk=0) -> np.ndarray:
+                          threads=0, chunk=None) -> np.ndarray:
     p = _pv(particles)
     n_sources = p.shape[0] if n_sources is None else n_sources
     S = default_segments(n_sources) if S is None else S
     t = np.ascontiguousarray(targets, dtype=np.int32)
     o = np.zeros(t.shape[0], dtype=POSVELO_DTYPE)
-    if chunk:
-        load().mapo_step_allpairs_targets_chunked(_ptr(p), n_sources, _ptr(t), t.shape[0], dt, damping, S, chunk,
-                                                  flavour, threads, _ptr(o))
-        return o
-    load().mapo_step_allpairs_targets(_ptr(p), n_sources, _ptr(t), t.shape[0], dt, damping, S, flavour,
-                                      threads, _ptr(o))
+    load().mapo_step_allpairs_targets_chunked(_ptr(p), n_sources, _ptr(t), t.shape[0], dt, damping, S, _chain(chunk),
+                                              flavour, threads, _ptr(o))
     return o
 
 
@@ -205,9 +207,37 @@ def step_well(particles, n_active=None, dt=0.1, damping=1.0, flavour=LITERAL, ou
     return o
 
 
+def per_body_report(got, ref, before, floor_frac=1e-3) -> dict:
+    """Per-body companion of rel_errors (which normalises by the GLOBAL maximum, so that `pos` -- of order
+    the sphere radius against displacements of order 1 -- can hardly fail):
+      accel_rel_l2_{p50,p99,max}  per body  |dv_got - dv_ref|_2 / max(|dv_ref|_2, floor), dv = velo - velo_before
+                                  (= accel * dt * damping: the acceleration itself), floor = floor_frac *
+                                  median |dv_ref|_2 so that bodies whose net force cancels do not divide by ~0
+      pos_ulp_max                 largest |pos_got - pos_ref|_inf in units of the fp32 spacing at the body's
+                                  largest coordinate: the step adds a displacement far smaller than pos, so
+                                  anything beyond a couple of ulps means a wrong displacement, not rounding
+      accel_len_rel_{p99,max}     per body |w_got - w_ref| / max(w_ref, floor) for pos.w = |accel|"""
+    g, r, b = _pv(got), _pv(ref), _pv(before)
+    dv_g = g["velo"][:, :3].astype(np.float64) - b["velo"][:, :3].astype(np.float64)
+    dv_r = r["velo"][:, :3].astype(np.float64) - b["velo"][:, :3].astype(np.float64)
+    mag = np.linalg.norm(dv_r, axis=1)
+    floor = floor_frac * float(np.median(mag)) if mag.size else 0.0
+    rel = np.linalg.norm(dv_g - dv_r, axis=1) / np.maximum(mag, max(floor, 1e-300))
+    pr = r["pos"][:, :3]
+    ulp = np.spacing(np.abs(pr).max(axis=1).astype(np.float32)).astype(np.float64)
+    pos_ulps = np.abs(g["pos"][:, :3].astype(np.float64) - pr.astype(np.float64)).max(axis=1) / ulp
+    w_g, w_r = g["pos"][:, 3].astype(np.float64), r["pos"][:, 3].astype(np.float64)
+    w_floor = floor_frac * float(np.median(w_r)) if w_r.size else 0.0
+    w_rel = np.abs(w_g - w_r) / np.maximum(w_r, max(w_floor, 1e-300))
+    return {"accel_rel_l2_p50": float(np.percentile(rel, 50)), "accel_rel_l2_p99": float(np.percentile(rel, 99)),
+            "accel_rel_l2_max": float(rel.max()), "pos_ulp_max": float(pos_ulps.max()),
+            "accel_len_rel_p99": float(np.percentile(w_rel, 99)), "accel_len_rel_max": float(w_rel.max())}
+
+
 def rel_errors(got, ref) -> dict:
     """Error metrics used by the parity tests (documented in DESIGN.md):
-    per quantity q in {pos.xyz, velo.xyz, pos.w}:  max_i |got_i - ref_i|_inf / max_i |ref_i|_inf."""
+    per quantity q in {pos.xyz, velo.xyz, pos.w}:  max_i |got_i - ref_i|_inf / max_i |ref_i|_inf.
+    The norm is global (the north star's "max relative error"); per_body_report() is the per-body view."""
     g, r = _pv(got), _pv(ref)
     out = {}
     for name, gq, rq in (("pos", g["pos"][:, :3], r["pos"][:, :3]),

@@ -8,8 +8,9 @@
 //
 // What is the reference's and what is ours:
 //   ref_body_body_interaction, ref_csmain, ref_constants   pure reference code
-//   ref_accel_allpairs / ref_step_allpairs                 OUR canonical loop (segments of 64-body
-//       tiles, partials summed left to right: DESIGN.md section 3) around the reference's
+//   ref_accel_allpairs / ref_step_allpairs                 OUR canonical loop (32 segments of 64-body
+//       tiles, chains of 2,048 sources folded left to right into the segment's partial, partials
+//       summed left to right: DESIGN.md section 3) around the reference's
 //       bodyBodyInteraction, and the reference's integration lines (:103-108) restated because
 //       CSMain fuses them with the gravity-well force.  The shipped CSMain has no all-pairs loop.
 #include <cstring>
@@ -32,7 +33,8 @@ void segment_range(int n_sources, int S, int s, int &j0, int &j1)
     j1 = (int)b;
 }
 
-float3 accel_of(const float *posvelo, int n_sources, int S, int i)
+// chain: sources per sequential accumulation (0 = one chain per segment)
+float3 accel_of(const float *posvelo, int n_sources, int S, int chain, int i)
 {
     const float *pi = posvelo + 8 * (size_t)i;
     const float4 bi(pi[0], pi[1], pi[2], pi[3]);
@@ -40,10 +42,17 @@ float3 accel_of(const float *posvelo, int n_sources, int S, int i)
     for (int s = 0; s < S; ++s) {
         int j0, j1;
         segment_range(n_sources, S, s, j0, j1);
+        const int step = (chain > 0 && j1 - j0 > chain) ? chain : (j1 - j0 > 0 ? j1 - j0 : 1);
         float3 partial;
-        for (int j = j0; j < j1; ++j) {
-            const float *pj = posvelo + 8 * (size_t)j;
-            bodyBodyInteraction(partial, float4(pj[0], pj[1], pj[2], pj[3]), bi, g_fParticleMass, 1);
+        for (int c0 = j0; c0 < j1; c0 += step) {
+            const int c1 = c0 + step < j1 ? c0 + step : j1;
+            float3 sum;
+            for (int j = c0; j < c1; ++j) {
+                const float *pj = posvelo + 8 * (size_t)j;
+                bodyBodyInteraction(sum, float4(pj[0], pj[1], pj[2], pj[3]), bi, g_fParticleMass, 1);
+            }
+            if (c0 == j0) partial = sum;
+            else partial += sum;
         }
         total += partial;
     }
@@ -96,7 +105,7 @@ void ref_csmain(const float *in_posvelo, float *out_posvelo, int n_dispatch, flo
     }
 }
 
-void ref_accel_allpairs(const float *posvelo, int n_sources, int S, const int *targets, int n_targets,
+void ref_accel_allpairs(const float *posvelo, int n_sources, int S, int chain, const int *targets, int n_targets,
                         float *accel3, int threads)
 {
 #ifdef _OPENMP
@@ -104,7 +113,7 @@ void ref_accel_allpairs(const float *posvelo, int n_sources, int S, const int *t
 #endif
 #pragma omp parallel for schedule(dynamic, 16) num_threads(threads)
     for (int k = 0; k < n_targets; ++k) {
-        const float3 a = accel_of(posvelo, n_sources, S, targets ? targets[k] : k);
+        const float3 a = accel_of(posvelo, n_sources, S, chain, targets ? targets[k] : k);
         accel3[3 * (size_t)k + 0] = a.x;
         accel3[3 * (size_t)k + 1] = a.y;
         accel3[3 * (size_t)k + 2] = a.z;
@@ -114,7 +123,7 @@ void ref_accel_allpairs(const float *posvelo, int n_sources, int S, const int *t
 // One all-pairs step of n_targets bodies (indices `targets`, or the first n_targets when null) against
 // the first n_sources; out_targets[k] receives the new state of target k.
 void ref_step_allpairs_targets(const float *in_posvelo, int n_sources, const int *targets, int n_targets, int S,
-                               float dt, float damping, int threads, float *out_targets)
+                               int chain, float dt, float damping, int threads, float *out_targets)
 {
 #ifdef _OPENMP
     if (threads <= 0) threads = omp_get_max_threads();
@@ -125,7 +134,7 @@ void ref_step_allpairs_targets(const float *in_posvelo, int n_sources, const int
         const float *p = in_posvelo + 8 * (size_t)i;
         float4 pos(p[0], p[1], p[2], p[3]);
         float3 vel(p[4], p[5], p[6]);
-        const float3 accel = accel_of(in_posvelo, n_sources, S, i);
+        const float3 accel = accel_of(in_posvelo, n_sources, S, chain, i);
         const float4 paramf(dt, damping, 0.f, 0.f);
         vel.xyz += accel.xyz * paramf.x;          // nBodyGravityCS.hlsl:103
         vel.xyz *= paramf.y;                      // :104

@@ -33,9 +33,9 @@ def load() -> ctypes.CDLL:
         lib.ref_constants.argtypes = [fp, fp]
         lib.ref_body_body_interaction.argtypes = [fp, fp, fp, c_float, c_int]
         lib.ref_csmain.argtypes = [c_void_p, c_void_p, c_int, c_float, c_float]
-        lib.ref_accel_allpairs.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int]
-        lib.ref_step_allpairs_targets.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_float, c_int,
-                                                  c_void_p]
+        lib.ref_accel_allpairs.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int]
+        lib.ref_step_allpairs_targets.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float,
+                                                  c_int, c_void_p]
         for f in (lib.ref_constants, lib.ref_body_body_interaction, lib.ref_csmain, lib.ref_accel_allpairs,
                   lib.ref_step_allpairs_targets):
             f.restype = None
@@ -75,7 +75,10 @@ def csmain(particles, n_dispatch=None, dt=0.1, damping=1.0) -> np.ndarray:
     return out
 
 
-def accel_allpairs(particles, S, n_sources=None, targets=None, threads=0) -> np.ndarray:
+CHAIN_SOURCES = 2048   # canonical chain length (include/mapc.h MAPC_CHAIN_SOURCES)
+
+
+def accel_allpairs(particles, S, n_sources=None, targets=None, threads=0, chain=CHAIN_SOURCES) -> np.ndarray:
     p = _pv(particles)
     n_sources = p.shape[0] if n_sources is None else n_sources
     if targets is None:
@@ -84,11 +87,13 @@ def accel_allpairs(particles, S, n_sources=None, targets=None, threads=0) -> np.
         t = np.ascontiguousarray(targets, dtype=np.int32)
         nt, tp = t.shape[0], t.ctypes.data_as(c_void_p)
     out = np.zeros((nt, 3), dtype=np.float32)
-    load().ref_accel_allpairs(p.ctypes.data_as(c_void_p), n_sources, S, tp, nt, out.ctypes.data_as(c_void_p), threads)
+    load().ref_accel_allpairs(p.ctypes.data_as(c_void_p), n_sources, S, chain, tp, nt, out.ctypes.data_as(c_void_p),
+                              threads)
     return out
 
 
-def step_allpairs_targets(particles, targets, S, n_sources=None, dt=0.1, damping=1.0, threads=0) -> np.ndarray:
+def step_allpairs_targets(particles, targets, S, n_sources=None, dt=0.1, damping=1.0, threads=0,
+                          chain=CHAIN_SOURCES) -> np.ndarray:
     """New state of the bodies `targets` (None = all) after one all-pairs step: OUR canonical loop around the
     reference's bodyBodyInteraction plus its integration lines (see ref_harness.cpp)."""
     p = _pv(particles)
@@ -99,10 +104,10 @@ def step_allpairs_targets(particles, targets, S, n_sources=None, dt=0.1, damping
         t = np.ascontiguousarray(targets, dtype=np.int32)
         nt, tp = t.shape[0], t.ctypes.data_as(c_void_p)
     out = np.zeros(nt, dtype=POSVELO_DTYPE)
-    load().ref_step_allpairs_targets(p.ctypes.data_as(c_void_p), n_sources, tp, nt, S, dt, damping, threads,
+    load().ref_step_allpairs_targets(p.ctypes.data_as(c_void_p), n_sources, tp, nt, S, chain, dt, damping, threads,
                                      out.ctypes.data_as(c_void_p))
     return out
 
 
-def step_allpairs(particles, S, dt=0.1, damping=1.0, threads=0) -> np.ndarray:
-    return step_allpairs_targets(particles, None, S, dt=dt, damping=damping, threads=threads)
+def step_allpairs(particles, S, dt=0.1, damping=1.0, threads=0, chain=CHAIN_SOURCES) -> np.ndarray:
+    return step_allpairs_targets(particles, None, S, dt=dt, damping=damping, threads=threads, chain=chain)

@@ -128,6 +128,8 @@ static inline unsigned long long load_acquire_sys(const unsigned long long *p)
 {
     return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 }
+static inline unsigned load_acquire_gpu(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void store_release_gpu(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 static inline void pdl_launch_dependents() {}
 static inline void pdl_wait() {}
 }  // namespace mapc

@@ -1,6 +1,6 @@
 // tests/emu/emu_asan_main.cpp -- TEST INFRASTRUCTURE ONLY: drives the emulated kernels (emu_kernels.cpp) over
-// every launch shape x {fused, unfused, mass-in-loop, chunk 256, chunk 2048, 4 ranks with the peer layout, TMA
-// staging, warp-shuffle broadcast} on
+// every launch shape x {fused, unfused, mass-in-loop, 256-source chains, a 2-slot scratch ring, 4 ranks with the
+// peer layout, TMA staging, warp-shuffle broadcast} on
 // exactly-sized heap buffers, for an AddressSanitizer + UBSan build (`make -C tests/emu asan`): any read or
 // write of the kernel source outside its buffers, and any signed overflow / misaligned access, aborts.
 #include <cstdio>
@@ -11,7 +11,8 @@
 struct PV { float pos[4]; float velo[4]; };
 extern "C" int emu_step_allpairs(const void *in, void *out, float *pos_next_out, int n, int n_active,
                       float dt, float damping, int S, int pairs, int threads, int fuse, int mass_in_loop,
-                      int world, int peer, int block_order, int chunk, int staging, unsigned long long *info);
+                      int world, int peer, int block_order, int chain, int staging, int ring_slots,
+                      unsigned long long *info);
 extern "C" int emu_step_well(const void *in, void *out, float *pos_next_out, float *packed_out, int n,
                   int n_active, float dt, float damping, int i_first, int n_local);
 int main() {
@@ -26,12 +27,12 @@ int main() {
         for (auto &sh : shapes)
             for (int S : {1, 2, 32})
                 for (int variant = 0; variant < 8; ++variant) {
-                    int fuse = variant != 1, inloop = variant == 2, chunk = variant == 3 ? 256 : (variant == 4 ? 2048 : 0);
+                    int fuse = variant != 1, inloop = variant == 2, chain = variant == 3 ? 256 : 2048, ring = variant == 4 ? 2 : 0;
                     int world = (variant == 5 && n == 2048 && S == 32) ? 4 : 1, peer = world > 1;
                     int staging = variant == 6 ? 1 : (variant == 7 ? 2 : 0);
                     if (staging == 1 && sh[1] * 2 * sh[0] < 512 && !(sh[0] == 2 && sh[1] == 128)) continue;   // TMA: 256-body-stage shapes only
                     if (staging == 2 && n > 1000) continue;                       // shuffles are slow to emulate
-                    int rc = emu_step_allpairs(in.data(), out.data(), mirror.data(), n, n, 0.1f, 1.f, S, sh[0], sh[1], fuse, inloop, world, peer, variant & 1, chunk, staging, info);
+                    int rc = emu_step_allpairs(in.data(), out.data(), mirror.data(), n, n, 0.1f, 1.f, S, sh[0], sh[1], fuse, inloop, world, peer, variant & 1, chain, staging, ring, info);
                     if (rc != 0) { printf("rc %d n %d S %d variant %d\n", rc, n, S, variant); return 1; }
                     ++runs;
                 }

@@ -28,14 +28,23 @@ namespace {
 using mapc::StepArgs;
 
 template <int P, int T, int TJ, int U, int MINB, int ORDER>
-bool launch_shape(bool fuse, bool peer, bool inloop, int chunk, int staging, bool has_tma, const StepArgs &a, int order)
+bool launch_shape(bool fuse, bool peer, bool inloop, int chain, int staging, bool has_tma, const StepArgs &a, int order)
 {
-    const dim3 grid((unsigned)a.n_iblocks, (unsigned)a.segs.count, 1), block(T, 1, 1);
+    // one cell per block, segment index fastest (csrc/mapc.cu launch_force)
+    const dim3 grid((unsigned)a.n_iblocks * (unsigned)a.segs.count, 1, 1), block(T, 1, 1);
     if (a.segs.count == 0 || a.i_cnt <= 0) return true;
+    if (chain == 256) {
+        // a short chain so that small problems have several chains per segment: fused / unfused default staging
+        if (peer || inloop || staging != 0) return false;
+        if (fuse) cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, false, false, false, false, 256>(a); });
+        else cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, false, false, false, false, false, 256>(a); });
+        return true;
+    }
+    if (chain != MAPC_CHAIN_SOURCES) return false;
     if (staging != 0) {
         // MAPC_TMA=1 / MAPC_SHFL=1: like csrc/mapc.cu, for the fused, non-peer, mass-per-partial kernel only;
         // TMA staging exists for the 256-body-stage shapes
-        if (!fuse || peer || inloop || chunk != 0) return false;
+        if (!fuse || peer || inloop) return false;
         if (staging == 1) {
             if (!has_tma) return false;
             cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, false, true>(a); });
@@ -44,16 +53,7 @@ bool launch_shape(bool fuse, bool peer, bool inloop, int chunk, int staging, boo
         }
         return true;
     }
-    if (chunk != 0) {
-        // MAPC_CHUNK=1: csrc/mapc.cu has it for the fused, non-peer, mass-per-partial kernel only, with
-        // 2,048-source chunks; 256 is instantiated here as well so that small problems have several chunks
-        if (!fuse || peer || inloop) return false;
-        if (chunk == 2048) cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, false, false, false, false, 2048>(a); });
-        else if (chunk == 256) cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, false, false, false, false, 256>(a); });
-        else return false;
-        return true;
-    }
-    // the instantiations csrc/mapc.cu launches (TMA and SHFL staging are hardware A/Bs, not emulated)
+    // the instantiations csrc/mapc.cu launches
     if (fuse && peer) cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, true>(a); });
     else if (fuse && inloop) cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, false, false, true>(a); });
     else if (fuse) cuda_emu::launch(grid, block, order, [&] { mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, true, false>(a); });
@@ -61,12 +61,12 @@ bool launch_shape(bool fuse, bool peer, bool inloop, int chunk, int staging, boo
     return true;
 }
 
-bool launch_force(int pairs, int threads, bool fuse, bool peer, bool inloop, int chunk, int staging, const StepArgs &a,
+bool launch_force(int pairs, int threads, bool fuse, bool peer, bool inloop, int chain, int staging, const StepArgs &a,
                   int order)
 {
 #define MAPC_SHAPE(P, T, TJ, U, MINB, ORDER, HAS_TMA) \
     if (pairs == P && threads == T)                   \
-        return launch_shape<P, T, TJ, U, MINB, ORDER>(fuse, peer, inloop, chunk, staging, HAS_TMA, a, order);
+        return launch_shape<P, T, TJ, U, MINB, ORDER>(fuse, peer, inloop, chain, staging, HAS_TMA, a, order);
 #include "../../multi-adapter-particles_b200/csrc/force_shapes.inc"
 #undef MAPC_SHAPE
     return false;
@@ -84,13 +84,17 @@ extern "C" {
 // .. world-1 wrote it (own shards only).  info[0] = kernel launches, info[1] = fence word after the step,
 // info[2] = 1 if every arrival counter and the `done` counter were back at zero.
 // peer: 0 NCCL layout, 1 peer layout (local + remote launch), 2 peer layout as one grid (MAPC_PEER_SINGLE=1).
-// chunk: 0, or the CHUNK template value (sources per bounded chain: 256 or 2048).
+// chain: sources per sequential accumulation chain: MAPC_CHAIN_SOURCES (the product) or 256 (so that small
+// problems have several chains per segment).
+// ring_slots: 0 = every target block its own scratch slot; > 0 = the scratch ring with that many slots
+// (ticket-ordered cells + slot_gen), as csrc/mapc.cu uses it for unsharded fused steps.
 // staging: 0 LDG/STS + LDS broadcast (default), 1 TMA bulk copies (MAPC_TMA=1), 2 warp-shuffle broadcast (MAPC_SHFL=1).
 // returns 0, or -1 for an unknown shape / variant, -2 for a layout the library would refuse (peer with
 // straddling segments)
 int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next_out, int n, int n_active,
                       float dt, float damping, int S, int pairs, int threads, int fuse, int mass_in_loop,
-                      int world, int peer, int block_order, int chunk, int staging, unsigned long long *info)
+                      int world, int peer, int block_order, int chain, int staging, int ring_slots,
+                      unsigned long long *info)
 {
     if (n % world) return -2;
     const int n_local = n / world;
@@ -117,28 +121,34 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
         std::vector<PV> in_local(n_local), out_local(n_local);
         std::memcpy(in_local.data(), in + i_first, (size_t)n_local * sizeof(PV));
         std::memcpy(out_local.data(), out + i_first, (size_t)n_local * sizeof(PV));
-        std::vector<float4> partial((size_t)S * n_local, make_float4(nan, nan, nan, nan));
+        const int n_iblocks = (n_targets + per_block - 1) / per_block;
+        const bool ring = ring_slots > 0 && ring_slots < n_iblocks && fuse && world == 1;
+        const int slots = ring ? ring_slots : n_iblocks;
+        std::vector<float4> partial((size_t)slots * S * per_block, make_float4(nan, nan, nan, nan));
         std::vector<float4> pos_next(n, make_float4(nan, nan, nan, nan));
         std::vector<unsigned> counters(n_local / 64 + 2, 0u);
-        unsigned done = 0;
+        std::vector<unsigned> slot_gen(slots, 0u);
+        unsigned done[2] = {0, 0};   // [0] target blocks integrated, [1] cell ticket
         unsigned long long stamps[2] = {0, 0};
 
         StepArgs a{};
         a.pos = packed[r].data();
         a.partial = partial.data();
-        a.partial_stride = n_local;
+        a.scratch_blocks = slots;
+        a.ticket = ring ? &done[1] : nullptr;
+        a.slot_gen = ring ? slot_gen.data() : nullptr;
         a.i_first = i_first;
         a.i_cnt = n_targets;
         a.n_sources = n_sources;
         a.S = S;
-        a.n_iblocks = (n_targets + per_block - 1) / per_block;
+        a.n_iblocks = n_iblocks;
         a.counters = counters.data();
         a.in = reinterpret_cast<const mapc_posvelo *>(in_local.data());
         a.out = reinterpret_cast<mapc_posvelo *>(out_local.data());
         a.pos_next = pos_next.data();
         a.dt = dt;
         a.damping = damping;
-        a.done = &done;
+        a.done = done;
         a.stamp_begin = fuse ? &stamps[0] : nullptr;
         a.stamp_end = fuse ? &stamps[1] : nullptr;
         a.fence_word = (fuse && world == 1) ? &fence_word : nullptr;
@@ -150,7 +160,7 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
                                                              /*gather_pending=*/world > 1 && !peer);
         const mapc::SegList &local = lay.local, &remote = lay.remote;
         const int *owner = lay.owner;
-        const bool peer_ok = peer && fuse && n_sources == n && !mass_in_loop && chunk == 0 && lay.aligned;
+        const bool peer_ok = peer && fuse && n_sources == n && !mass_in_loop && chain == MAPC_CHAIN_SOURCES && lay.aligned;
         if (peer && world > 1 && !peer_ok && remote.count > 0) return -2;
 
         if (peer == 2 && peer_ok && world > 1 && remote.count > 0) {
@@ -168,11 +178,11 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
             }
             a.flag_expect = 7;
             a.segs = all;
-            if (!launch_force(pairs, threads, fuse, true, mass_in_loop, chunk, 0, a, block_order)) return -1;
+            if (!launch_force(pairs, threads, fuse, true, mass_in_loop, chain, 0, a, block_order)) return -1;
             ++launches;
         } else {
         a.segs = local;
-        if (!launch_force(pairs, threads, fuse, false, mass_in_loop, chunk, staging, a, block_order)) return -1;
+        if (!launch_force(pairs, threads, fuse, false, mass_in_loop, chain, staging, a, block_order)) return -1;
         launches += (local.count > 0);
         if (local.count > 0) a.stamp_begin = nullptr;
         if (remote.count > 0) {
@@ -185,19 +195,20 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
                 }
                 a.flag_expect = 7;
             }
-            if (!launch_force(pairs, threads, fuse, use_peer, mass_in_loop, chunk, use_peer ? 0 : staging, a, block_order)) return -1;
+            if (!launch_force(pairs, threads, fuse, use_peer, mass_in_loop, chain, use_peer ? 0 : staging, a, block_order)) return -1;
             ++launches;
         }
         }
         if (!fuse) {
             // MAPC_FUSE=0: the separate combine + integrate, as csrc/mapc.cu launches it
             cuda_emu::launch(dim3((n_targets + 255) / 256), dim3(256), 0, [&] {
-                mapc::integrate_kernel(a.in, a.out, a.pos_next, a.partial, n_local, S, i_first, n_targets, dt, damping);
+                mapc::integrate_kernel(a.in, a.out, a.pos_next, a.partial, per_block, S, i_first, n_targets, dt, damping);
             });
             ++launches;
         }
         for (unsigned c : counters) counters_clean = counters_clean && c == 0u;
-        counters_clean = counters_clean && done == 0u;
+        counters_clean = counters_clean && done[0] == 0u && done[1] == 0u;
+        for (unsigned g : slot_gen) counters_clean = counters_clean && g == 0u;
         if (fuse && !(stamps[0] != 0 && stamps[1] >= stamps[0])) counters_clean = false;
         std::memcpy(out + i_first, out_local.data(), (size_t)n_local * sizeof(PV));
         for (int i = 0; i < n_local; ++i) std::memcpy(pos_next_out + 4 * (size_t)(i_first + i), &pos_next[i_first + i], 16);

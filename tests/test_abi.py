@@ -45,8 +45,9 @@ def test_plan_segments_matches_oracle_rule(mapc, oracle):
     for n in (1, 64, 1000, 10_000, 131_071, 131_072, 262_144, 262_145, 524_288, 524_289, 741_376, 1_048_576,
               2_097_153, 4_194_304, 8_000_000):
         assert mapc.plan_segments(n) == oracle.default_segments(n)
-    assert [mapc.plan_segments(n) for n in (10_000, 262_144, 370_688, 524_288, 741_376, 1_048_576, 4_194_304)] == \
-        [32, 32, 64, 64, 128, 128, 128]
+    # the frozen canonical order: 32 segments for every N, chains of 2,048 sources
+    assert {mapc.plan_segments(n) for n in (10_000, 262_144, 370_688, 524_288, 741_376, 1_048_576, 4_194_304)} == {32}
+    assert mapc.plan_chain_sources() == oracle.default_chain() == 2048
 
 
 def test_no_cpu_fallback(mapc):
@@ -115,6 +116,7 @@ int main(void) {
     memset(&p, 0, sizeof p); memset(&h, 0, sizeof h);
     if (sizeof(mapc_posvelo) != 32) return 2;
     if (mapc_plan_segments(262144u) != 32 || mapc_plan_segments(4194304u) != MAPC_MAX_SEGMENTS) return 3;
+    if (mapc_plan_chain_sources() != MAPC_CHAIN_SOURCES) return 3;
     if (mapc_compute_create(&c, 0u, 0, 0) != MAPC_ERR_INVALID_ARGUMENT) return 4;
     if (strstr(mapc_last_error(), "num_particles") == 0) return 5;
     printf("%s\n", mapc_version());

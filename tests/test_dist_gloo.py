@@ -97,14 +97,15 @@ def test_local_segment_classification(mapc):
 def test_canonical_segments_partition_the_sources(mapc, oracle):
     """Properties of the canonical segmentation that every size must satisfy: the S ranges tile [0, n)
     exactly, in order, on 64-body boundaries (only the last may be ragged), the three statements of the rule
-    (library, oracle, host helper) agree, and no chain is longer than 8,192 sources while S < 128."""
+    (library, oracle, host helper) agree, and S is the frozen 32 for every size (chains are bounded separately,
+    at 2,048 sources inside a segment)."""
     from hypothesis import given, settings, strategies as st
 
     @settings(max_examples=200, deadline=None, derandomize=True)
     @given(st.integers(min_value=1, max_value=5_000_000))
     def check(n):
         S = mapc.plan_segments(n)
-        assert S == oracle.default_segments(n) and S in (32, 64, 128)
+        assert S == oracle.default_segments(n) == 32
         edge, longest = 0, 0
         for s in range(S):
             a, b = mapc.dist.segment_range(n, S, s)
@@ -112,8 +113,7 @@ def test_canonical_segments_partition_the_sources(mapc, oracle):
             assert a == edge and b >= a and (b % 64 == 0 or b == n)
             edge, longest = b, max(longest, b - a)
         assert edge == n
-        if n <= 128 * 8192:
-            assert longest <= 8192 + 64       # +64: a boundary is rounded down to a whole tile
+        assert longest <= (n + 63) // 64 // S * 64 + 64     # segments differ by at most one tile
     check()
 
 

@@ -30,7 +30,7 @@ def emu():
     lib = ctypes.CDLL(os.path.join(EMU_DIR, "libmapc_emu.so"))
     vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     lib.emu_step_allpairs.restype = ci
-    lib.emu_step_allpairs.argtypes = [vp, vp, vp, ci, ci, cf, cf, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+    lib.emu_step_allpairs.argtypes = [vp, vp, vp, ci, ci, cf, cf, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
     lib.emu_make_plan.restype = None
     lib.emu_make_plan.argtypes = [ci, ci, ci, ci, ci, vp]
     lib.emu_local_targets.restype = ci
@@ -40,9 +40,13 @@ def emu():
     return lib
 
 
+CHAIN = 2048     # include/mapc.h MAPC_CHAIN_SOURCES: the product's chain length
+
+
 def emu_step(lib, particles, S, shape, n_active=None, dt=0.1, damping=1.0, fuse=True, mass_in_loop=False,
-             world=1, peer=False, block_order=0, stale=None, chunk=0, staging=0):
-    """-> (written side, packed mirror, info) after one emulated step."""
+             world=1, peer=False, block_order=0, stale=None, chunk=CHAIN, staging=0, ring=0):
+    """-> (written side, packed mirror, info) after one emulated step.  chunk: sources per chain (2048, or 256
+    so that small problems have several chains per segment); ring: slots of the scratch ring (0 = none)."""
     n = particles.shape[0]
     n_active = n if n_active is None else n_active
     inp = np.ascontiguousarray(particles)
@@ -51,12 +55,12 @@ def emu_step(lib, particles, S, shape, n_active=None, dt=0.1, damping=1.0, fuse=
     info = np.zeros(3, dtype=np.uint64)
     rc = lib.emu_step_allpairs(inp.ctypes.data, out.ctypes.data, mirror.ctypes.data, n, n_active, dt, damping, S,
                                shape[0], shape[1], int(fuse), int(mass_in_loop), world, int(peer), block_order,
-                               chunk, staging, info.ctypes.data)
+                               chunk, staging, ring, info.ctypes.data)
     assert rc == 0, f"emu_step_allpairs returned {rc}"
     return out, mirror, info
 
 
-def oracle_step(oracle, particles, S, n_active=None, dt=0.1, damping=1.0, stale=None, flavour=None, chunk=0):
+def oracle_step(oracle, particles, S, n_active=None, dt=0.1, damping=1.0, stale=None, flavour=None, chunk=CHAIN):
     out = stale.copy() if stale is not None else particles.copy()
     return oracle.step_allpairs(particles, n_active=n_active, dt=dt, damping=damping, S=S,
                                 flavour=oracle.MIRRORED if flavour is None else flavour, out=out, chunk=chunk)
@@ -180,10 +184,10 @@ def test_well_and_pack_kernels(emu, oracle, mapc, n, n_active, shard):
 
 @pytest.mark.parametrize("shape", SHAPES)
 def test_chunked_order_equals_chunked_oracle_bitwise(emu, oracle, mapc, shape):
-    """The experimental bounded-chain order (kernel template flag CHUNK, MAPC_CHUNK=1; oracle `chunk`): chunk
-    sums folded left to right into the segment partial.  N = 1,100 with 256-source chunks: S = 1 gives one
-    segment of 4 full chunks + a ragged one, S = 2 segments of 576 and 524 (2 chunks + remainder), S = 32
-    segments shorter than a chunk (then nothing changes and the result equals the unchunked order)."""
+    """The chains of the canonical order (kernel template parameter CHAIN; oracle `chunk`): chain sums folded
+    left to right into the segment's partial.  N = 1,100 with 256-source chains: S = 1 gives one segment of 4
+    full chains + a ragged one, S = 2 segments of 576 and 524 (2 chains + remainder), S = 32 segments shorter
+    than a chain (then the chain length does not matter and the result equals the 2,048-source order)."""
     n = 1100
     p = mapc.ic.plummer(n, 80.0, seed=5)
     for S in (1, 2, 32):
@@ -200,16 +204,33 @@ def test_chunked_order_equals_chunked_oracle_bitwise(emu, oracle, mapc, shape):
 
 
 def test_chunked_order_product_chunk_size_and_shards(emu, oracle, mapc):
-    """The chunk size the library uses (2,048 sources), on segments of 2,560 sources (N = 5,120, S = 2), and
-    the same through two emulated ranks (local + remote launches fold into the same partials)."""
+    """The chain length the library uses (2,048 sources), on segments of 2,560 sources (N = 5,120, S = 2), and
+    the same through two emulated ranks (local + remote launches write the same partials)."""
     n = 5120
     p = mapc.ic.uniform_sphere(n, 600.0, seed=13, speed=1.0)
-    ref = oracle_step(oracle, p, 2, chunk=2048)
-    assert ref.tobytes() != oracle_step(oracle, p, 2).tobytes()
-    got, _, _ = emu_step(emu, p, 2, (4, 256), chunk=2048)
+    ref = oracle_step(oracle, p, 2)
+    assert ref.tobytes() != oracle_step(oracle, p, 2, chunk=0).tobytes()     # the chains really change the bits
+    got, _, _ = emu_step(emu, p, 2, (4, 256))
     assert got.tobytes() == ref.tobytes()
-    got2, mirror2, info2 = emu_step(emu, p, 2, (2, 128), chunk=2048, world=2)
+    got2, mirror2, info2 = emu_step(emu, p, 2, (2, 128), world=2)
     assert got2.tobytes() == ref.tobytes() and mirror2.tobytes() == ref["pos"].tobytes() and info2[2] == 1
+
+
+@pytest.mark.parametrize("shape,n", [((1, 32), 700), ((2, 64), 1100), ((4, 128), 5120)])
+def test_scratch_ring_does_not_change_bits(emu, oracle, mapc, shape, n):
+    """The L2-resident scratch ring of unsharded fused steps (csrc/mapc.cu plan_scratch): `ring` slots reused
+    round-robin by the target blocks, cells handed out by the ticket counter in (target block, segment) order,
+    a slot released by the combine of the block that used it before.  Whatever the ring size and whichever
+    order the blocks start in, the bits are those of one slot per target block; ticket, slot generations and
+    counters are back at zero for the next step."""
+    p = mapc.ic.uniform_sphere(n, 300.0, seed=n, speed=1.0)
+    S = mapc.plan_segments(n)
+    ref = oracle_step(oracle, p, S)
+    for ring in (1, 2, 3):
+        for order in (0, 1):
+            got, mirror, info = emu_step(emu, p, S, shape, ring=ring, block_order=order)
+            assert got.tobytes() == ref.tobytes(), (ring, order)
+            assert mirror.tobytes() == ref["pos"].tobytes() and info[2] == 1 and info[1] == 42
 
 
 def test_bounded_chains_cut_the_rounding_noise(oracle, mapc):
@@ -288,9 +309,8 @@ def test_launch_plan_and_dispatch_granularity(emu, oracle, mapc):
 
     # config 3: 262,144 targets, S = 32 -> (4, 256), 128 target blocks x 32 segments = 4,096 cells
     assert plan(262_144, 32) == (4, 256, 128, 32)
-    # an 8-GPU shard of the weak-scaled size: 92,672 targets are exactly 181 blocks of (2, 128), which beats
-    # the 1.6 % of idle lanes (4, 256) would leave in its 46th block
-    assert plan(92_672, 128) == (2, 128, 181, 128)
+    # an 8-GPU shard of config 5 (4,194,304 / 8 targets): 256 target blocks of (4, 256)
+    assert plan(524_288, 32) == (4, 256, 256, 32)
     # every shape can be forced, and covers all targets
     for pairs, threads in SHAPES:
         pl = plan(10_000, 32, (pairs, threads))
@@ -341,20 +361,18 @@ def test_fuzz_emulated_kernel_against_oracle(emu, oracle, mapc):
     from hypothesis import given, settings, strategies as st, HealthCheck
 
     @settings(max_examples=150, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
-    @given(n=st.integers(1, 700), S=st.integers(1, 40), shape=st.sampled_from(SHAPES),
-           frac=st.floats(0.0, 1.0), fuse=st.booleans(), chunk=st.sampled_from([0, 0, 256]),
-           seed=st.integers(0, 1000))
-    def check(n, S, shape, frac, fuse, chunk, seed):
-        if chunk and not fuse:
-            chunk = 0
+    @given(n=st.integers(1, 700), S=st.integers(1, 32), shape=st.sampled_from(SHAPES),
+           frac=st.floats(0.0, 1.0), fuse=st.booleans(), chunk=st.sampled_from([CHAIN, CHAIN, 256]),
+           ring=st.sampled_from([0, 0, 1, 2, 5]), seed=st.integers(0, 1000))
+    def check(n, S, shape, frac, fuse, chunk, ring, seed):
         n_active = max(1, min(n, int(round(frac * n)))) if frac < 0.9 else n
         p = mapc.ic.uniform_sphere(n, 150.0, seed=seed, speed=1.0)
         stale = p.copy()
         stale["velo"] -= 2.0
         got, _, info = emu_step(emu, p, S, shape, n_active=n_active, fuse=fuse, stale=stale, chunk=chunk,
-                                dt=0.07, damping=0.99)
+                                ring=ring, dt=0.07, damping=0.99)
         ref = oracle_step(oracle, p, S, n_active=n_active, stale=stale, chunk=chunk, dt=0.07, damping=0.99)
-        assert got.tobytes() == ref.tobytes(), (n, S, shape, n_active, fuse, chunk, seed)
+        assert got.tobytes() == ref.tobytes(), (n, S, shape, n_active, fuse, chunk, ring, seed)
         assert info[2] == 1
     check()
 
@@ -366,7 +384,7 @@ def test_fuzz_sharded_layouts_against_oracle(emu, oracle, mapc):
     from hypothesis import given, settings, strategies as st, HealthCheck
 
     @settings(max_examples=60, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
-    @given(world=st.sampled_from([2, 3, 4, 8]), k=st.integers(1, 5), S=st.integers(1, 48),
+    @given(world=st.sampled_from([2, 3, 4, 8]), k=st.integers(1, 5), S=st.integers(1, 32),
            shape=st.sampled_from(SHAPES), peer=st.booleans(), seed=st.integers(0, 1000))
     def check(world, k, S, shape, peer, seed):
         n = 64 * world * k
@@ -376,7 +394,7 @@ def test_fuzz_sharded_layouts_against_oracle(emu, oracle, mapc):
         mirror = np.full((n, 4), np.nan, dtype=np.float32)
         info = np.zeros(3, dtype=np.uint64)
         rc = emu.emu_step_allpairs(inp.ctypes.data, out.ctypes.data, mirror.ctypes.data, n, n, 0.1, 1.0, S,
-                                   shape[0], shape[1], 1, 0, world, int(peer), 0, 0, 0, info.ctypes.data)
+                                   shape[0], shape[1], 1, 0, world, int(peer), 0, CHAIN, 0, 0, info.ctypes.data)
         if peer and rc == -2:
             # segments straddle shards: the library refuses the peer exchange for such a step
             count = n // world

@@ -73,34 +73,37 @@ def test_golden_fixtures(oracle, name):
     assert state.view(np.float32).tobytes() == g["literal_last"].tobytes()
 
 
-def test_segment_rule_bounds_rounding_noise_on_close_pair_targets(oracle, mapc):
-    """Why mapc_plan_segments keeps chains at <= 8,192 sources.
+def test_chain_rule_bounds_rounding_noise_on_close_pair_targets(oracle, mapc):
+    """Why the canonical order bounds every sequential chain at 2,048 sources.
 
     The targets that set the max-norm parity figure are the few with a neighbour inside a few softening
-    lengths: after that neighbour the segment's fp32 accumulator is large and every later term of the chain
+    lengths: after that neighbour the chain's fp32 accumulator is large and every later term of the chain
     is rounded at that magnitude.  On the N = 262,144 bench workload the 1,024 targets with the closest
     neighbours reproduce the all-target figure (the worst target is among them): the two correctly rounded
-    CPU flavours differ by 4.6e-6 with the canonical S = 32 and by 1.07e-5 -- the size of the 1e-5 gate --
-    with the 32,768-term chains of S = 8.  A random subsample of targets sees neither."""
+    CPU flavours differ by 2.5e-6 in the canonical order, by 4.6e-6 with one 8,192-term chain per segment
+    (the rule of round 1) and by 1.07e-5 -- the size of the 1e-5 gate -- with 32,768-term chains (S = 8, no
+    chains).  With bounded chains the segment count no longer matters.  A random subsample sees none of it."""
     from scipy.spatial import cKDTree
     p = mapc.ic.workload("sphere_262144")
     n = p.shape[0]
-    assert oracle.default_segments(n) == 32
+    assert oracle.default_segments(n) == 32 and oracle.default_chain() == 2048
     xyz = p["pos"][:, :3].astype(np.float64)
     dist, _ = cKDTree(xyz).query(xyz, k=2)
     close = np.sort(np.argsort(dist[:, 1])[:1024]).astype(np.int32)
     assert dist[close, 1].max() < 25.0          # all of them have a neighbour within five softening lengths
 
-    def envelope(S):
-        lit = oracle.step_allpairs_targets(p, close, S=S, flavour=oracle.LITERAL)
-        mir = oracle.step_allpairs_targets(p, close, S=S, flavour=oracle.MIRRORED)
+    def envelope(S, chunk):
+        lit = oracle.step_allpairs_targets(p, close, S=S, flavour=oracle.LITERAL, chunk=chunk)
+        mir = oracle.step_allpairs_targets(p, close, S=S, flavour=oracle.MIRRORED, chunk=chunk)
         return max(oracle.rel_errors(mir, lit).values())
 
-    e32, e8 = envelope(32), envelope(8)
-    assert e32 < 6e-6, e32
-    assert e8 > 1.5 * e32, (e8, e32)
+    canonical = envelope(32, None)
+    one_chain_32, one_chain_8 = envelope(32, 0), envelope(8, 0)
+    assert canonical < 4e-6, canonical
+    assert one_chain_32 > 1.5 * canonical and one_chain_8 > 3 * canonical, (canonical, one_chain_32, one_chain_8)
+    assert envelope(8, None) < 4e-6             # bounded chains: the segment count no longer matters
     rng = np.random.default_rng(0)
     rnd = np.sort(rng.choice(n, 1024, replace=False)).astype(np.int32)
     lit = oracle.step_allpairs_targets(p, rnd, flavour=oracle.LITERAL)
     mir = oracle.step_allpairs_targets(p, rnd, flavour=oracle.MIRRORED)
-    assert max(oracle.rel_errors(mir, lit).values()) < e32
+    assert max(oracle.rel_errors(mir, lit).values()) < canonical

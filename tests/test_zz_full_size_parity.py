@@ -4,13 +4,15 @@ Collected last on purpose (file name): it is the longest test of the suite -- 6.
 on the host cores, 11 oracle steps, about a minute with the vectorised oracle -- so everything else has
 reported before it starts.
 
-Why it exists: a 2048-target subsample (test_gpu_parity.py) misses the handful of targets with a neighbour
-inside a few softening lengths, and those carry the largest rounding error of the whole step -- once such a
-neighbour has made a segment's fp32 accumulator large, every later term of that chain is rounded at that
-magnitude.  The canonical segment rule (mapc_plan_segments: chains of at most 8,192 sources) is sized from
-this: two correctly rounded CPU evaluations of the same formula (LITERAL vs MIRRORED) differ by 1.07e-5 over
-all targets with 32,768-term chains and by 4.6e-6 with 8,192-term chains.
+Why it exists: a random 2048-target subsample misses the handful of targets with a neighbour inside a few
+softening lengths, and those carry the largest rounding error of the whole step -- once such a neighbour has
+made a chain's fp32 accumulator large, every later term of that chain is rounded at that magnitude.  The
+canonical order (32 segments, chains of 2,048 sources) is sized from this: two correctly rounded CPU
+evaluations of the same formula (LITERAL vs MIRRORED) differ by 1.07e-5 over all targets with 32,768-term
+chains, by 4.6e-6 with 8,192-term chains and by 2.5e-6 with the 2,048-term chains that are now the rule.
+(The sizes above, configs 4 and 5, are covered on their closest-neighbour targets in test_gpu_parity.py.)
 """
+import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -32,10 +34,21 @@ def gpu_steps(mapc, particles, steps):
 def test_full_size_262144_one_step_all_targets(mapc, oracle, gpu):
     p = mapc.ic.workload("sphere_262144")           # the bench workload (bench.py, config 3)
     assert mapc.plan_segments(p.shape[0]) == oracle.default_segments(p.shape[0]) == 32
+    assert mapc.plan_chain_sources() == oracle.default_chain() == 2048
     got = gpu_steps(mapc, p, 1)
-    err = oracle.rel_errors(got, oracle.step_allpairs(p, flavour=oracle.LITERAL))
-    print("N=262,144, all targets, 1 step:", err)
+    ref = oracle.step_allpairs(p, flavour=oracle.LITERAL)
+    err = oracle.rel_errors(got, ref)
+    body = oracle.per_body_report(got, ref, p)
+    print("N=262,144, all targets, 1 step: global", err, "per-body", body)
     assert max(err.values()) <= TOL_1, err
+    assert body["accel_rel_l2_p99"] <= TOL_1 and body["pos_ulp_max"] <= 2.0, body
+    # the scratch ring (the default at this size: 128 target blocks share 32 slots) changes no bit
+    import os
+    try:
+        os.environ["MAPC_RING"] = "0"
+        assert gpu_steps(mapc, p, 1).tobytes() == got.tobytes()
+    finally:
+        os.environ.pop("MAPC_RING", None)
 
 
 def test_full_size_262144_ten_steps_all_targets_lattice(mapc, oracle, gpu):
@@ -52,26 +65,23 @@ def test_full_size_262144_ten_steps_all_targets_lattice(mapc, oracle, gpu):
     assert max(err.values()) <= TOL_10, err
 
 
-@pytest.mark.xfail(strict=False, reason="experimental opt-in variant (MAPC_CHUNK=1): verified against the oracle by "
-                   "CPU emulation only so far; informational until its first run on hardware")
-def test_experimental_bounded_chain_order(mapc, oracle, gpu):
-    """MAPC_CHUNK=1: chains bounded at 2,048 sources.  N = 131,072 with S = 32 gives
-    segments of 4,096 sources = two chunks each, so the order really differs from the default; the result must
-    match the oracle's `chunk=2048` order like the default matches the plain one."""
-    import os
+def test_bounded_chains_are_the_canonical_order(mapc, oracle, gpu):
+    """N = 131,072 gives segments of 4,096 sources = two 2,048-source chains each, so the chain fold really
+    runs: the result must match the oracle's canonical order (both flavours at the 1e-5 gate) and must NOT
+    be what one chain per segment would give."""
     n = 131_072
     p = mapc.ic.uniform_sphere(n, 6350.0, seed=5)
-    default = gpu_steps(mapc, p, 1)
-    try:
-        os.environ["MAPC_CHUNK"] = "1"
-        chunked = gpu_steps(mapc, p, 1)
-    finally:
-        os.environ.pop("MAPC_CHUNK", None)
-    assert chunked.tobytes() != default.tobytes()
-    lit = oracle.step_allpairs(p, flavour=oracle.LITERAL, chunk=2048)
-    mir = oracle.step_allpairs(p, flavour=oracle.MIRRORED, chunk=2048)
-    err_l, err_m = oracle.rel_errors(chunked, lit), oracle.rel_errors(chunked, mir)
-    print("MAPC_CHUNK=1 vs chunked oracle: literal", err_l, "mirrored", err_m)
+    got = gpu_steps(mapc, p, 1)
+    lit = oracle.step_allpairs(p, flavour=oracle.LITERAL)
+    mir = oracle.step_allpairs(p, flavour=oracle.MIRRORED)
+    err_l, err_m = oracle.rel_errors(got, lit), oracle.rel_errors(got, mir)
+    print("canonical order vs oracle: literal", err_l, "mirrored", err_m)
     # both at the 1e-5 gate: over ALL targets the distance to MIRRORED is set by the same chain noise as the
     # distance to LITERAL (MUFU.RSQ perturbs every term, after which the roundings of the chain decorrelate)
     assert max(err_l.values()) <= TOL_1 and max(err_m.values()) <= TOL_1, (err_l, err_m)
+    one_chain = oracle.step_allpairs(p, flavour=oracle.MIRRORED, chunk=0)
+    assert one_chain.tobytes() != mir.tobytes()
+    # the kernel is closer to the canonical order than to the one-chain order in the mean
+    d_can = np.abs(got["velo"][:, :3].astype(np.float64) - mir["velo"][:, :3]).mean()
+    d_one = np.abs(got["velo"][:, :3].astype(np.float64) - one_chain["velo"][:, :3]).mean()
+    assert d_can < d_one, (d_can, d_one)

@@ -180,7 +180,6 @@ void run_force(const float4 *pos, float4 *partial, int n, Timer &t)
     mapc::StepArgs args{};
     args.pos = pos;
     args.partial = partial;
-    args.partial_stride = n;
     args.i_first = 0;
     args.i_cnt = n_tgt;
     args.n_sources = n;
@@ -189,13 +188,14 @@ void run_force(const float4 *pos, float4 *partial, int n, Timer &t)
     for (int s = 0; s < S; ++s) args.segs.ids[s] = s;
     const int per_block = T * 2 * P;
     args.n_iblocks = (n_tgt + per_block - 1) / per_block;
+    args.scratch_blocks = args.n_iblocks;
     auto kernel = mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, false, false, TMA, INLOOP>;
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, T, 0));
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, kernel));
     const long long cells = (long long)args.n_iblocks * S;
-    const dim3 grid(args.n_iblocks, S);
+    const dim3 grid(args.n_iblocks * S);
     const float ms = t.best([&] { kernel<<<grid, T>>>(args); }, 4);
     const double ginter = (double)n * n_tgt / (ms * 1e-3) / 1e9;
     printf("force %s %s %s P=%d T=%3d TJ=%3d U=%d minB=%2d regs=%3d occ=%2d blk/SM (%2d warps) cells=%5lld : %8.3f ms %8.1f G int/s %5.1f %% of %.2f TF\n",
@@ -208,7 +208,7 @@ int main(int argc, char **argv)
     const int n = argc > 1 ? atoi(argv[1]) : 262144;
     g_targets = argc > 2 ? atoi(argv[2]) : 0;
     g_segments = argc > 3 ? atoi(argv[3]) : 32;
-    if (g_segments < 1 || g_segments > 64) { fprintf(stderr, "S must be in 1..64\n"); return 2; }
+    if (g_segments < 1 || g_segments > MAPC_MAX_SEGMENTS) { fprintf(stderr, "S must be in 1..32\n"); return 2; }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     g_sms = prop.multiProcessorCount;
@@ -460,16 +460,17 @@ int main(int argc, char **argv)
         CK(cudaMalloc(&partial2, sizeof(float4) * n * 8));
         const int n_tgt = g_targets > 0 ? g_targets : n;
         mapc::StepArgs args{};
-        args.pos = pos; args.partial_stride = n; args.i_first = 0; args.i_cnt = n_tgt; args.n_sources = n; args.S = 8;
+        args.pos = pos; args.i_first = 0; args.i_cnt = n_tgt; args.n_sources = n; args.S = 8;
         args.segs.count = 8;
         for (int sgm = 0; sgm < 8; ++sgm) args.segs.ids[sgm] = sgm;
         args.n_iblocks = (n_tgt + 2047) / 2048;
+        args.scratch_blocks = args.n_iblocks;
         CK(cudaMemset(partial, 0, sizeof(float4) * n * 8));
         CK(cudaMemset(partial2, 0, sizeof(float4) * n * 8));
         args.partial = partial;
-        mapc::force_cells_kernel<4, 256, 256, 8, 2, 0, false, false, false, false><<<dim3(args.n_iblocks, 8), 256>>>(args);
+        mapc::force_cells_kernel<4, 256, 256, 8, 2, 0, false, false, false, false><<<dim3(args.n_iblocks * 8), 256>>>(args);
         args.partial = partial2;
-        mapc::force_cells_kernel<4, 256, 256, 8, 2, 0, false, false, true, false><<<dim3(args.n_iblocks, 8), 256>>>(args);
+        mapc::force_cells_kernel<4, 256, 256, 8, 2, 0, false, false, true, false><<<dim3(args.n_iblocks * 8), 256>>>(args);
         CK(cudaDeviceSynchronize());
         std::vector<float4> a((size_t)n * 8), b((size_t)n * 8);
         CK(cudaMemcpy(a.data(), partial, sizeof(float4) * a.size(), cudaMemcpyDeviceToHost));

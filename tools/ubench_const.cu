@@ -111,15 +111,15 @@ void run_smem(const float4 *pos, float4 *partial, int n, int S, Timer &t)
     mapc::StepArgs args{};
     args.pos = pos;
     args.partial = partial;
-    args.partial_stride = n;
     args.i_cnt = n;
     args.n_sources = n;
     args.S = S;
     args.segs.count = S;
     for (int s = 0; s < S; ++s) args.segs.ids[s] = s;
     args.n_iblocks = (n + T * 2 * P - 1) / (T * 2 * P);
+    args.scratch_blocks = args.n_iblocks;
     auto kernel = mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, false>;
-    const dim3 grid(args.n_iblocks, S);
+    const dim3 grid(args.n_iblocks * S);
     const float ms = t.best([&] { kernel<<<grid, T>>>(args); });
     const double ginter = (double)n * n / (ms * 1e-3) / 1e9;
     printf("smem-src  %s P=%d T=%3d U=%d minB=%2d                              : %8.3f ms %8.1f G int/s %5.1f %%\n",
