@@ -1714,65 +1714,27 @@ mapc_status mapc_consumer_latest(mapc_consumer *r, const float **host_positions,
 }
 
 // ---- initial conditions (InitializeParticles / LoadParticles) -----------------------------------
-namespace {
-
-// fast_rand(), Compute.cpp:605-609: g_seed = 214013*g_seed + 2531011; (g_seed >> 16) & 0x7FFF
-struct FastRand {
-    uint32_t state;
-    int next()
-    {
-        state = 214013u * state + 2531011u;
-        return (int)((state >> 16) & 0x7FFF);
-    }
-};
-
-// LoadParticles, USE_SCALAR_OPTIMIZED branch (Compute.cpp:719-749): random walk until |delta|^2 >= 10,
-// project on the shell of radius `spread` around `center`, velocity = cross(dir, perp) * speed with
-// dir = normalize(position), perp = normalize((1,1,1) - dir).  The reference's *Est normalisations
-// (rsqrtps, ~12 bit) are replaced by exact ones; its per-thread unseeded LCG by one seeded stream.
-void load_particles(mapc_posvelo *out, uint32_t count, float cx, float cy, float cz, float speed,
-                    float spread, FastRand &rng)
-{
-    const float k_scale = (1.f / 32767.f) * 2.f;  // (1/RAND_MAX)*2 with MSVC's RAND_MAX (Compute.cpp:721)
-    for (uint32_t i = 0; i < count; ++i) {
-        float dx = (float)rng.next() * k_scale - 1.f;
-        float dy = (float)rng.next() * k_scale - 1.f;
-        float dz = (float)rng.next() * k_scale - 1.f;
-        while (dx * dx + dy * dy + dz * dz < 10.f) {  // Compute.cpp:728
-            dx += (float)rng.next() * k_scale - 1.f;
-            dy += (float)rng.next() * k_scale - 1.f;
-            dz += (float)rng.next() * k_scale - 1.f;
-        }
-        const float inv = spread / sqrtf(dx * dx + dy * dy + dz * dz);
-        const float px = cx + dx * inv, py = cy + dy * inv, pz = cz + dz * inv;
-        const float il = 1.f / sqrtf(px * px + py * py + pz * pz);
-        const float ux = px * il, uy = py * il, uz = pz * il;           // direction (:746)
-        float qx = 1.f - ux, qy = 1.f - uy, qz = 1.f - uz;               // (1,1,1) - direction (:747)
-        const float iq = 1.f / sqrtf(qx * qx + qy * qy + qz * qz);
-        qx *= iq; qy *= iq; qz *= iq;
-        out[i].pos[0] = px; out[i].pos[1] = py; out[i].pos[2] = pz; out[i].pos[3] = 0.f;
-        out[i].velo[0] = (uy * qz - uz * qy) * speed;                    // cross(direction, perp) (:748)
-        out[i].velo[1] = (uz * qx - ux * qz) * speed;
-        out[i].velo[2] = (ux * qy - uy * qx) * speed;
-        out[i].velo[3] = 0.f;
-    }
-}
-
-}  // namespace
-
+// Generated ON the device (init_particles_kernel, one thread per particle): the reference fills two host
+// vectors with a parallel_for and uploads them (Compute.cpp:820-923); at 4 M bodies that is 134 MB of H2D
+// this path does not need.  Every rank of a sharded handle generates all N positions (it needs them as
+// sources) and the PosVelo of its own shard; oracle/oracle.c mapo_init_particles restates the same bytes.
 mapc_status mapc_compute_init_particles(mapc_compute *c, uint32_t seed)
 {
     if (!c) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL handle");
-    std::vector<mapc_posvelo> host(c->n);  // value-initialised like vector::resize (Compute.cpp:825-829)
-    memset(host.data(), 0, host.size() * sizeof(mapc_posvelo));
-    FastRand rng{seed};
+    MAPC_TRY(mapc::require_ungated(&c->gcompute, "InitializeParticles"));
+    DeviceGuard g(c->device);
+    MAPC_CUDA(cudaStreamSynchronize(c->comm));
     // Compute.cpp:831-844: two groups of N/2 around x = +-0.75*ParticleSpread
     const float center = MAPC_PARTICLE_SPREAD * 0.750f;
-    const uint32_t half = c->n / 2;
-    load_particles(host.data(), half, center, 0.f, 0.f, MAPC_INITIAL_PARTICLE_SPEED, MAPC_PARTICLE_SPREAD, rng);
-    load_particles(host.data() + half, half, -center, 0.f, 0.f, MAPC_INITIAL_PARTICLE_SPEED,
-                   MAPC_PARTICLE_SPREAD, rng);
-    return mapc_compute_upload(c, host.data(), c->n);
+    mapc::init_particles_kernel<<<(c->n + 255) / 256, 256, 0, c->compute>>>(
+        c->posvelo[0], c->posvelo[1], c->packed[0], c->packed[1], c->n, c->i_first, c->n_local, seed, center,
+        MAPC_INITIAL_PARTICLE_SPEED, MAPC_PARTICLE_SPREAD);
+    MAPC_CUDA(cudaGetLastError());
+    ++c->launches;
+    c->gather_pending[0] = c->gather_pending[1] = false;
+    MAPC_TRY(mapc_compute_wait_for_gpu(c));  // InitializeParticles ends with WaitForGpu, Compute.cpp:922
+    c->has_state = true;
+    return MAPC_OK;
 }
 
 }  // extern "C"

@@ -635,6 +635,85 @@ well_step_kernel(const mapc_posvelo *__restrict__ in, mapc_posvelo *__restrict__
     pos_next[i_first + i] = pos_out;
 }
 
+// ---- initial conditions: InitializeParticles / LoadParticles, USE_SCALAR_OPTIMIZED branch ---------------------
+// Particles/Compute.cpp:596-609 fast_rand (g_seed = 214013*g_seed + 2531011; (g_seed >> 16) & 0x7FFF),
+// :719-749 random walk until |delta|^2 >= 10, project on the shell of radius `spread` around `center`,
+// velocity = cross(direction, perp) * speed, direction = normalize(position), perp = normalize((1,1,1) - direction);
+// :831-844 two groups of N/2 around x = +-0.75 * ParticleSpread.
+// The reference draws from an unseeded thread_local LCG inside a parallel_for, so its particles depend on the
+// thread schedule and no run can be reproduced.  Here every particle owns an LCG stream seeded from (seed, i)
+// -- one thread per particle, any order, same bits -- and the *Est normalisations (rsqrtps, ~12 bits) are
+// exact; every operation is an IEEE round-to-nearest op with no contraction, so the CPU restatement
+// (oracle/oracle.c mapo_init_particles) produces the same bytes.
+__host__ __device__ inline unsigned ic_stream_seed(unsigned seed, unsigned i)
+{
+    unsigned s = seed + 0x9E3779B9u * (i + 1u);
+    s ^= s >> 16;
+    s *= 0x85EBCA6Bu;
+    s ^= s >> 13;
+    s *= 0xC2B2AE35u;
+    s ^= s >> 16;
+    return s;
+}
+
+__device__ __forceinline__ float ic_rand_pm1(unsigned &state)
+{
+    state = 214013u * state + 2531011u;                       // fast_rand(), Compute.cpp:605-609
+    const int r = (int)((state >> 16) & 0x7FFFu);
+    const float k_scale = (1.f / 32767.f) * 2.f;              // (1/RAND_MAX)*2, MSVC RAND_MAX (Compute.cpp:721)
+    return __fadd_rn(__fmul_rn((float)r, k_scale), -1.f);
+}
+
+__device__ __forceinline__ float ic_dot3(float x, float y, float z)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+// Thread i generates body i of all n (both groups): its position goes to packed_a/packed_b[i] (every rank
+// needs all positions as sources); bodies of the shard [i_first, i_first + n_local) also get their PosVelo
+// on both ping-pong sides (Compute.cpp:881-882, :903-904 initialise both sides alike).
+__global__ void __launch_bounds__(256)
+init_particles_kernel(mapc_posvelo *__restrict__ side_a, mapc_posvelo *__restrict__ side_b,
+                      float4 *__restrict__ packed_a, float4 *__restrict__ packed_b, unsigned n, unsigned i_first,
+                      unsigned n_local, unsigned seed, float center_x, float speed, float spread)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned half = n / 2u;
+    float4 pos = make_float4(0.f, 0.f, 0.f, 0.f), vel = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < 2u * half) {   // an odd N leaves its last body zero, like the value-initialised vector (Compute.cpp:825-829)
+        const float cx = i < half ? center_x : -center_x;      // Compute.cpp:831-844
+        unsigned state = ic_stream_seed(seed, i);
+        float dx = ic_rand_pm1(state), dy = ic_rand_pm1(state), dz = ic_rand_pm1(state);
+        while (ic_dot3(dx, dy, dz) < 10.f) {                    // Compute.cpp:728
+            dx = __fadd_rn(dx, ic_rand_pm1(state));
+            dy = __fadd_rn(dy, ic_rand_pm1(state));
+            dz = __fadd_rn(dz, ic_rand_pm1(state));
+        }
+        const float len = __fsqrt_rn(ic_dot3(dx, dy, dz));     // XMVector3Normalize, then * spread (:738-739)
+        const float px = __fadd_rn(cx, __fmul_rn(__fdiv_rn(dx, len), spread));
+        const float py = __fmul_rn(__fdiv_rn(dy, len), spread);
+        const float pz = __fmul_rn(__fdiv_rn(dz, len), spread);
+        const float pl = __fsqrt_rn(ic_dot3(px, py, pz));
+        const float ux = __fdiv_rn(px, pl), uy = __fdiv_rn(py, pl), uz = __fdiv_rn(pz, pl);   // direction (:746)
+        float qx = __fadd_rn(1.f, -ux), qy = __fadd_rn(1.f, -uy), qz = __fadd_rn(1.f, -uz);   // (1,1,1) - direction (:747)
+        const float ql = __fsqrt_rn(ic_dot3(qx, qy, qz));
+        qx = __fdiv_rn(qx, ql); qy = __fdiv_rn(qy, ql); qz = __fdiv_rn(qz, ql);
+        pos = make_float4(px, py, pz, 0.f);
+        vel.x = __fmul_rn(__fadd_rn(__fmul_rn(uy, qz), -__fmul_rn(uz, qy)), speed);           // cross * speed (:748)
+        vel.y = __fmul_rn(__fadd_rn(__fmul_rn(uz, qx), -__fmul_rn(ux, qz)), speed);
+        vel.z = __fmul_rn(__fadd_rn(__fmul_rn(ux, qy), -__fmul_rn(uy, qx)), speed);
+    }
+    packed_a[i] = pos;
+    packed_b[i] = pos;
+    if (i >= i_first && i - i_first < n_local) {
+        float4 *a = reinterpret_cast<float4 *>(side_a + (i - i_first));
+        float4 *b = reinterpret_cast<float4 *>(side_b + (i - i_first));
+        a[0] = pos; a[1] = vel;
+        b[0] = pos; b[1] = vel;
+    }
+}
+
 // packed float4 position mirror from a PosVelo array (after upload / state copy)
 __global__ void __launch_bounds__(256)
 pack_positions_kernel(const mapc_posvelo *__restrict__ in, float4 *__restrict__ pos, int n)

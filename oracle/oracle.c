@@ -368,3 +368,58 @@ void mapo_step_well(const mapo_posvelo *in, mapo_posvelo *out, int n, int n_acti
         mapo_integrate(&in[i], accel, dt, damping, flavour, &out[i]);
     }
 }
+
+/* ---- initial conditions (Compute.cpp:596-609, :719-749, :820-844) --------------------------------------- */
+static unsigned ic_stream_seed(unsigned seed, unsigned i)
+{
+    unsigned s = seed + 0x9E3779B9u * (i + 1u);   /* one stream per particle (the reference's is per thread, unseeded) */
+    s ^= s >> 16;
+    s *= 0x85EBCA6Bu;
+    s ^= s >> 13;
+    s *= 0xC2B2AE35u;
+    s ^= s >> 16;
+    return s;
+}
+
+static float ic_rand_pm1(unsigned *state)
+{
+    *state = 214013u * *state + 2531011u;                     /* fast_rand(), :605-609 */
+    const int r = (int)((*state >> 16) & 0x7FFFu);
+    const float k_scale = (1.f / 32767.f) * 2.f;              /* (1.f / RAND_MAX) * 2.f with MSVC's RAND_MAX, :721 */
+    return ((float)r * k_scale) - 1.f;                        /* :723-725 */
+}
+
+static float ic_dot3(float x, float y, float z) { return (x * x + y * y) + z * z; }
+
+void mapo_init_particles(mapo_posvelo *out, unsigned n, unsigned seed)
+{
+    const float spread = 400.0f;                              /* defines.h:42 PARTICLE_SPREAD */
+    const float speed = 15.0f;                                /* defines.h:39 INITIAL_PARTICLE_SPEED */
+    const float center = spread * 0.750f;                     /* Compute.cpp:831 */
+    const unsigned half = n / 2u;
+    memset(out, 0, (size_t)n * sizeof(*out));                 /* vector::resize value-initialises, :825-829 */
+    for (unsigned i = 0; i < 2u * half; ++i) {
+        const float cx = i < half ? center : -center;         /* :832-844 */
+        unsigned state = ic_stream_seed(seed, i);
+        float dx = ic_rand_pm1(&state), dy = ic_rand_pm1(&state), dz = ic_rand_pm1(&state);
+        while (ic_dot3(dx, dy, dz) < 10.f) {                  /* :728 */
+            dx += ic_rand_pm1(&state);                        /* :730-735 */
+            dy += ic_rand_pm1(&state);
+            dz += ic_rand_pm1(&state);
+        }
+        const float len = sqrtf(ic_dot3(dx, dy, dz));         /* XMVector3Normalize :738 */
+        const float px = cx + (dx / len) * spread;            /* :739-742 */
+        const float py = (dy / len) * spread;
+        const float pz = (dz / len) * spread;
+        const float pl = sqrtf(ic_dot3(px, py, pz));
+        const float ux = px / pl, uy = py / pl, uz = pz / pl; /* direction, :746 (exact instead of NormalizeEst) */
+        float qx = 1.f - ux, qy = 1.f - uy, qz = 1.f - uz;    /* (1,1,1) - direction, :747 */
+        const float ql = sqrtf(ic_dot3(qx, qy, qz));
+        qx /= ql; qy /= ql; qz /= ql;
+        out[i].pos[0] = px; out[i].pos[1] = py; out[i].pos[2] = pz; out[i].pos[3] = 0.f;
+        out[i].velo[0] = (uy * qz - uz * qy) * speed;         /* cross(direction, perp) * initialSpeed, :748 */
+        out[i].velo[1] = (uz * qx - ux * qz) * speed;
+        out[i].velo[2] = (ux * qy - uy * qx) * speed;
+        out[i].velo[3] = 0.f;
+    }
+}

@@ -107,6 +107,12 @@ void mapo_step_allpairs_targets_chunked(const mapo_posvelo *in, int n_sources,
 void mapo_step_well(const mapo_posvelo *in, mapo_posvelo *out, int n, int n_active,
                     float dt, float damping, int flavour);
 
+/* InitializeParticles / LoadParticles (Compute.cpp:596-609 fast_rand, :719-749 USE_SCALAR_OPTIMIZED branch,
+ * :831-844 two groups around x = +-0.75 * ParticleSpread), with one LCG stream per particle seeded from
+ * (seed, i) -- the reference's generator is unseeded and thread-schedule dependent -- and exact
+ * normalisations where the reference uses the *Est forms.  Plain IEEE float ops in the written order. */
+void mapo_init_particles(mapo_posvelo *out, unsigned n, unsigned seed);
+
 int  mapo_max_threads(void);
 
 #ifdef __cplusplus

@@ -74,6 +74,8 @@ def load() -> ctypes.CDLL:
                                                c_int, c_int, c_void_p]
     lib.mapo_step_well.restype = None
     lib.mapo_step_well.argtypes = [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int]
+    lib.mapo_init_particles.restype = None
+    lib.mapo_init_particles.argtypes = [c_void_p, ctypes.c_uint, ctypes.c_uint]
     lib.mapo_max_threads.restype = c_int
     lib.mapo_max_threads.argtypes = []
     _lib = lib
@@ -232,6 +234,13 @@ def per_body_report(got, ref, before, floor_frac=1e-3) -> dict:
     return {"accel_rel_l2_p50": float(np.percentile(rel, 50)), "accel_rel_l2_p99": float(np.percentile(rel, 99)),
             "accel_rel_l2_max": float(rel.max()), "pos_ulp_max": float(pos_ulps.max()),
             "accel_len_rel_p99": float(np.percentile(w_rel, 99)), "accel_len_rel_max": float(w_rel.max())}
+
+
+def init_particles(n: int, seed: int) -> np.ndarray:
+    """The reference's initial conditions (two shells, Compute.cpp:719-749, :820-844), seeded per particle."""
+    out = np.zeros(n, dtype=POSVELO_DTYPE)
+    load().mapo_init_particles(_ptr(out), n, seed & 0xFFFFFFFF)
+    return out
 
 
 def rel_errors(got, ref) -> dict:

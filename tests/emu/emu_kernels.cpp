@@ -249,6 +249,19 @@ int emu_step_well(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next_out
     return 0;
 }
 
+// init_particles_kernel for the shard [i_first, i_first + n_local) of n bodies: side_a / side_b n_local PosVelo
+// each, packed_a / packed_b n float4 each.
+int emu_init_particles(mapc_posvelo *side_a, mapc_posvelo *side_b, float *packed_a, float *packed_b, unsigned n,
+                       unsigned i_first, unsigned n_local, unsigned seed)
+{
+    cuda_emu::launch(dim3((n + 255) / 256), dim3(256), 0, [&] {
+        mapc::init_particles_kernel(side_a, side_b, reinterpret_cast<float4 *>(packed_a), reinterpret_cast<float4 *>(packed_b),
+                                    n, i_first, n_local, seed, MAPC_PARTICLE_SPREAD * 0.750f, MAPC_INITIAL_PARTICLE_SPEED,
+                                    MAPC_PARTICLE_SPREAD);
+    });
+    return 0;
+}
+
 // csrc/step_layout.hpp make_plan / local_targets, for the host-logic tests: out = {pairs, threads, blocks_x, S}
 void emu_make_plan(int n_targets, int S, int sm_count, int force_pairs, int force_threads, int *out)
 {

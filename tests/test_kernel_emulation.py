@@ -37,6 +37,8 @@ def emu():
     lib.emu_local_targets.argtypes = [ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ci]
     lib.emu_step_well.restype = ci
     lib.emu_step_well.argtypes = [vp, vp, vp, vp, ci, ci, cf, cf, ci, ci]
+    lib.emu_init_particles.restype = ci
+    lib.emu_init_particles.argtypes = [vp, vp, vp, vp, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]
     return lib
 
 
@@ -180,6 +182,29 @@ def test_well_and_pack_kernels(emu, oracle, mapc, n, n_active, shard):
     assert got[:first].tobytes() == stale[:first].tobytes()                        # another rank's shard
     assert mirror[lo:hi].tobytes() == ref["pos"][lo:hi].tobytes()
     assert packed.tobytes() == p["pos"].tobytes()
+
+
+@pytest.mark.parametrize("n,first,count", [(1000, 0, 1000), (1001, 0, 1001), (4096, 1024, 1024)])
+def test_init_particles_kernel_equals_oracle_restatement_bitwise(emu, oracle, mapc, n, first, count):
+    """init_particles_kernel (the reference's two-shell initial conditions, Compute.cpp:719-749 / :820-844,
+    generated on the device) against the oracle's restatement: same bytes, on a whole handle, an odd N (the
+    last body stays zero) and the second shard of four (PosVelo local, packed positions for all N)."""
+    ref = oracle.init_particles(n, 1234)
+    a = np.zeros(count, dtype=mapc.POSVELO_DTYPE)
+    b = np.zeros(count, dtype=mapc.POSVELO_DTYPE)
+    pa = np.full((n, 4), np.nan, dtype=np.float32)
+    pb = np.full((n, 4), np.nan, dtype=np.float32)
+    assert emu.emu_init_particles(a.ctypes.data, b.ctypes.data, pa.ctypes.data, pb.ctypes.data, n, first, count, 1234) == 0
+    assert a.tobytes() == ref[first:first + count].tobytes() and b.tobytes() == a.tobytes()
+    assert pa.tobytes() == ref["pos"].tobytes() and pb.tobytes() == pa.tobytes()
+    # the distribution the reference describes: two shells of radius 400 around x = +-300, speed <= 15, tangential
+    half = n // 2
+    for sl, cx in ((slice(0, half), 300.0), (slice(half, 2 * half), -300.0)):
+        d = ref["pos"][sl, :3] - np.array([cx, 0, 0], dtype=np.float32)
+        np.testing.assert_allclose(np.linalg.norm(d, axis=1), 400.0, rtol=1e-5)
+    speed = np.linalg.norm(ref["velo"][:, :3], axis=1)
+    assert speed.max() <= 15.0 * (1 + 1e-5) and speed.mean() > 5.0
+    assert oracle.init_particles(n, 1235).tobytes() != ref.tobytes()
 
 
 @pytest.mark.parametrize("shape", SHAPES)
