@@ -136,8 +136,10 @@ MAPC_API mapc_status mapc_compute_ipc_attach(mapc_compute *c, const void *blobs_
 MAPC_API mapc_status mapc_compute_destroy(mapc_compute *c);
 
 /* Upload of initial state into BOTH sides of the ping-pong (Compute.cpp:881-882, :903-904).
- * `host` holds all N bodies (global indexing) even for a sharded handle: every rank needs all
- * positions as sources.  Blocks until the copy is complete, as InitializeParticles does
+ * `host` points at body 0 of all N (global indexing).  An unsharded handle reads all of it; a sharded
+ * handle reads ONLY its own shard, host[first .. first+count), and obtains the other ranks' positions by
+ * an all-gather on the device -- so the call is collective over the ranks, and the rest of `host` need
+ * not even be valid on that rank.  Blocks until the state is in place, as InitializeParticles does
  * (Compute.cpp:922). */
 MAPC_API mapc_status mapc_compute_upload(mapc_compute *c, const mapc_posvelo *host, uint32_t n);
 /* Current state (the side the last Simulate wrote) of bodies [first, first+count) -> host.
@@ -241,6 +243,20 @@ typedef struct mapc_consumer mapc_consumer;
  * fence to `producer` (GetSharedHandles), adopts its buffer index (SetShared, Render.cpp:222-224)
  * and copies the initial positions into both local buffers. */
 MAPC_API mapc_status mapc_consumer_create(mapc_consumer **out, mapc_compute *producer, int device);
+/* The same with flags.  MAPC_CONSUMER_ASYNC is the reference's async mode -- renderer and simulation on ONE
+ * adapter (Particles::ShareHandles, Particles.cpp:202-207; Compute::SetAsync, Compute.cpp:956-987;
+ * Render::Draw, Render.cpp:849-852 and :928-932): no copy stream and no local buffers, the consumer reads
+ * the producer's packed positions in place after waiting for compute fence F-1, waits for F before it signals
+ * its render fence, and hands the RENDER fence value back for Simulate to wait on.  `device` must be the
+ * producer's.  (The reference aliases the renderer's buffers into the compute object and copies them back
+ * in ResetFromAsyncHelper, Compute.cpp:260-298; with CUDA both sides address the producer's buffers, so
+ * there is nothing to alias or to restore when the consumer goes away.)  The frame a Draw dumps is then
+ * the result of the previous Simulate (one step of latency instead of two).
+ * A sharded producer is allowed in both modes: the consumer then sees that rank's shard only
+ * (counts passed to mapc_consumer_draw stay global and are clipped to the shard). */
+#define MAPC_CONSUMER_ASYNC 1u
+MAPC_API mapc_status mapc_consumer_create_ex(mapc_consumer **out, mapc_compute *producer, int device,
+                                             uint32_t flags);
 MAPC_API mapc_status mapc_consumer_destroy(mapc_consumer *r);
 /* HANDLE Render::Draw(int numActive, Particles*, UINT64& inout_fenceValue, int numCopied),
  * Render.cpp:839-938, non-async path.  in: the fence value the upcoming Simulate will signal;
@@ -254,7 +270,8 @@ MAPC_API mapc_status mapc_consumer_latest(mapc_consumer *r, const float **host_p
                                           uint64_t *frame, uint32_t *count);
 /* Protocol counters for logs and tests: out[0] copy fence completed, out[1] copy fence value issued,
  * out[2] render fence completed, out[3] render fence value to be issued next, out[4] shared buffer
- * index, out[5] current (local) buffer index, out[6] frames drawn, out[7] copies issued. */
+ * index, out[5] current (local) buffer index, out[6] frames drawn, out[7] device-to-device copies issued by
+ * Draw (always 0 for an async consumer). */
 MAPC_API mapc_status mapc_consumer_counters(const mapc_consumer *r, uint64_t out[8]);
 /* Render::WaitForGpu, Render.cpp:626-647: drains copy and render streams */
 MAPC_API mapc_status mapc_consumer_wait_for_gpu(mapc_consumer *r);

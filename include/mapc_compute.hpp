@@ -120,7 +120,11 @@ private:
 // The consumer role of Particles/Render.{h,cpp}, headless (see mapc_consumer_* in mapc.h)
 class HeadlessRender {
 public:
-    HeadlessRender(Compute &compute, int device) { ThrowIfFailed(mapc_consumer_create(&m_handle, compute.Handle(), device)); }
+    // in_asyncMode: Render::SetAsyncMode(true) -- consumer and producer on one device, no copies (Particles.cpp:202-207)
+    HeadlessRender(Compute &compute, int device, bool in_asyncMode = false)
+    {
+        ThrowIfFailed(mapc_consumer_create_ex(&m_handle, compute.Handle(), device, in_asyncMode ? MAPC_CONSUMER_ASYNC : 0u));
+    }
     ~HeadlessRender() { mapc_consumer_destroy(m_handle); }
     HeadlessRender(const HeadlessRender &) = delete;
     HeadlessRender &operator=(const HeadlessRender &) = delete;

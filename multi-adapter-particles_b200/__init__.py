@@ -42,6 +42,7 @@ IPC_BLOB_BYTES = 256
 
 FORCE_ALLPAIRS = 0
 FORCE_WELL = 1
+CONSUMER_ASYNC = 1      # mapc_consumer_create_ex flag: the reference's async mode (same device, no copies)
 
 #: numpy view of ``struct PosVelo { float4 pos; float4 velo; }`` (ParticleShared.hlsl:12-16)
 POSVELO_DTYPE = np.dtype([("pos", np.float32, 4), ("velo", np.float32, 4)])
@@ -68,7 +69,7 @@ EXPORTED_SYMBOLS = (
     "mapc_consumer_create", "mapc_consumer_destroy", "mapc_consumer_draw", "mapc_consumer_latest",
     "mapc_consumer_wait_for_gpu", "mapc_consumer_counters",
     "mapc_compute_ipc_export", "mapc_compute_ipc_attach", "mapc_compute_simulate_steps",
-    "mapc_compute_exchange_times", "mapc_plan_chain_sources",
+    "mapc_compute_exchange_times", "mapc_plan_chain_sources", "mapc_consumer_create_ex",
 )
 
 
@@ -163,6 +164,7 @@ def load() -> ctypes.CDLL:
         "mapc_compute_simulate_steps": (c_int, [c_void_p, c_int, c_float, c_float, c_uint64, c_int]),
         "mapc_compute_exchange_times": (c_int, [c_void_p, P(c_float), P(c_float)]),
         "mapc_plan_chain_sources": (c_int, []),
+        "mapc_consumer_create_ex": (c_int, [P(c_void_p), c_void_p, c_int, c_uint32]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -414,11 +416,15 @@ class Consumer:
     copy stream pulls each step's positions to its own device and dumps them to pinned host memory,
     with the reference's copy-fence / render-fence protocol and one-frame latency."""
 
-    def __init__(self, compute: Compute, device: int = 0):
+    def __init__(self, compute: Compute, device: int = 0, async_mode: bool = False):
+        """``async_mode``: the reference's same-adapter mode (``Render::SetAsyncMode``, Render.cpp:849-852,
+        :928-932): no copy stream, the producer's buffers are read in place."""
         self._lib = load()
         self._h = c_void_p()
         self._compute = compute
-        _check(self._lib.mapc_consumer_create(byref(self._h), compute._h, device))
+        self.async_mode = bool(async_mode)
+        _check(self._lib.mapc_consumer_create_ex(byref(self._h), compute._h, device,
+                                                 CONSUMER_ASYNC if async_mode else 0))
 
     def Draw(self, in_numActiveParticles: int, inout_fenceValue: int, in_numParticlesCopied: int | None = None) -> int:
         """``Render::Draw``; returns the fence value to hand to ``Compute.Simulate``."""

@@ -53,6 +53,7 @@ struct mapc_fence {
     cudaStream_t light_stream = nullptr;
     int light_device = -1;
     uint64_t light_value = 0;                     // highest value signalled this way
+    uint64_t light_floor = 0;                     // values <= this were not (they predate the first light signal)
 };
 
 namespace mapc {

@@ -213,7 +213,12 @@ mapc_status fence_submit_signal(mapc_fence *f, cudaStream_t stream, int device, 
 
 mapc_status fence_submit_wait(mapc_fence *f, cudaStream_t stream, uint64_t value)
 {
-    if (fence_completed(f) >= value) return MAPC_OK;
+    // A completed value needs no wait -- unless it was signalled by a kernel writing the word itself: then the
+    // word says "the step is done", and the waiting stream still gets a CUDA-visible edge to the signalling
+    // stream (an event, below), so a copy engine never reads the step's output on the strength of a host-side
+    // poll alone.
+    const bool light = f->light_stream != nullptr && value <= f->light_value && value > f->light_floor;
+    if (!light && fence_completed(f) >= value) return MAPC_OK;
     for (const FenceSignal &sig : f->signals)
         if (sig.value >= value) {
             MAPC_CUDA(cudaStreamWaitEvent(stream, sig.event, 0));
@@ -251,6 +256,7 @@ static mapc_status run_op(GatedStream *gs, StreamOp &op)
             f->spare_device.push_back(f->signals.front().device);
             f->signals.pop_front();
         }
+        if (f->light_stream == nullptr) f->light_floor = op.value - 1;   // values below were signalled by stream operations
         f->light_stream = gs->stream;
         f->light_device = gs->device;
         if (op.value > f->light_value) f->light_value = op.value;
@@ -445,7 +451,6 @@ struct mapc_compute {
     size_t partial_bytes = 0;
     unsigned *slot_gen = nullptr;                   // scratch ring: target blocks combined out of each slot
     int slot_gen_count = 0;
-    mapc_posvelo *upload_stage = nullptr;           // sharded handles: landing buffer of Upload (all N)
     unsigned *counters = nullptr;                   // per target block: segments finished this step
     int counters_key = 0;                           // block size the counters were last used with
 
@@ -882,7 +887,6 @@ mapc_status mapc_compute_destroy(mapc_compute *c)
     if (c->counters) cudaFree(c->counters);
     if (c->done) cudaFree(c->done);
     if (c->stamps) cudaFreeHost(c->stamps);
-    if (c->upload_stage) cudaFree(c->upload_stage);
     if (c->ev_integrated) cudaEventDestroy(c->ev_integrated);
     for (int k = 0; k < mapc_compute::kTimerSlots; ++k) {
         if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]);
@@ -906,22 +910,37 @@ mapc_status mapc_compute_upload(mapc_compute *c, const mapc_posvelo *host, uint3
     if (n != c->n) return fail(MAPC_ERR_INVALID_ARGUMENT, "upload of %u bodies into a handle of %u", n, c->n);
     MAPC_TRY(mapc::require_ungated(&c->gcompute, "Upload"));
     DeviceGuard g(c->device);
-    // All N bodies land on the device once, then fan out: both PosVelo sides get the shard, both packed
-    // sides all N positions.  Unsharded, side 0 itself is the landing buffer; a sharded handle keeps a
-    // staging buffer for the bodies it does not own (allocated on first use, reused afterwards).
-    mapc_posvelo *all = c->posvelo[0];
-    if (c->world > 1) {
-        if (!c->upload_stage) MAPC_CUDA(cudaMalloc(&c->upload_stage, (size_t)n * sizeof(mapc_posvelo)));
-        all = c->upload_stage;
-    }
-    MAPC_CUDA(cudaMemcpyAsync(all, host, (size_t)n * sizeof(mapc_posvelo), cudaMemcpyHostToDevice, c->compute));
-    for (int s = 0; s < 2; ++s) {
-        if (c->posvelo[s] != all)
-            MAPC_CUDA(cudaMemcpyAsync(c->posvelo[s], all + c->i_first, (size_t)c->n_local * sizeof(mapc_posvelo),
-                                      cudaMemcpyDeviceToDevice, c->compute));
-        mapc::pack_positions_kernel<<<(n + 255) / 256, 256, 0, c->compute>>>(all, c->packed[s], (int)n);
+    if (c->world == 1) {
+        // side 0 is the landing buffer; side 1 and both packed mirrors fan out on the device
+        MAPC_CUDA(cudaMemcpyAsync(c->posvelo[0], host, (size_t)n * sizeof(mapc_posvelo), cudaMemcpyHostToDevice, c->compute));
+        MAPC_CUDA(cudaMemcpyAsync(c->posvelo[1], c->posvelo[0], (size_t)n * sizeof(mapc_posvelo),
+                                  cudaMemcpyDeviceToDevice, c->compute));
+        for (int s = 0; s < 2; ++s) {
+            mapc::pack_positions_kernel<<<(n + 255) / 256, 256, 0, c->compute>>>(c->posvelo[0], c->packed[s], (int)n);
+            MAPC_CUDA(cudaGetLastError());
+            ++c->launches;
+        }
+    } else {
+        // Sharded: a rank reads ONLY its own shard from `host` (n_local x 32 B of H2D instead of N x 32 B),
+        // packs its positions and the ranks all-gather the N x 16 B position array on the device.  Collective:
+        // every rank of the communicator must call Upload.
+        MAPC_CUDA(cudaStreamSynchronize(c->comm));
+        MAPC_CUDA(cudaMemcpyAsync(c->posvelo[0], host + c->i_first, (size_t)c->n_local * sizeof(mapc_posvelo),
+                                  cudaMemcpyHostToDevice, c->compute));
+        MAPC_CUDA(cudaMemcpyAsync(c->posvelo[1], c->posvelo[0], (size_t)c->n_local * sizeof(mapc_posvelo),
+                                  cudaMemcpyDeviceToDevice, c->compute));
+        mapc::pack_positions_kernel<<<(c->n_local + 255) / 256, 256, 0, c->compute>>>(
+            c->posvelo[0], c->packed[0] + c->i_first, (int)c->n_local);
         MAPC_CUDA(cudaGetLastError());
         ++c->launches;
+        MAPC_CUDA(cudaEventRecord(c->ev_integrated, c->compute));
+        MAPC_CUDA(cudaStreamWaitEvent(c->comm, c->ev_integrated, 0));
+        MAPC_NCCL(g_nccl.AllGather(c->packed[0] + c->i_first, c->packed[0], (size_t)c->n_local * 4, ncclFloat,
+                                   c->nccl, c->comm));
+        MAPC_CUDA(cudaEventRecord(c->ev_gathered[0], c->comm));
+        MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_gathered[0], 0));
+        MAPC_CUDA(cudaMemcpyAsync(c->packed[1], c->packed[0], (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice,
+                                  c->compute));
     }
     MAPC_CUDA(cudaStreamSynchronize(c->comm));
     c->gather_pending[0] = c->gather_pending[1] = false;
@@ -1020,9 +1039,14 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
     const uint32_t r = 1u - b;  // read side (reads 1-b, writes b)
     bool use_peer = false;
 
+    if (c->peer_mode && mode == MAPC_FORCE_WELL)
+        // a well step would overwrite this rank's packed positions without waiting for the peers that may
+        // still be reading them over NVLink (only the fused all-pairs step carries that wait, in its cells)
+        return fail(MAPC_ERR_UNSUPPORTED, "MAPC_FORCE_WELL steps are not available while the peer exchange is attached");
     if (n_targets > 0) {
         if (mode == MAPC_FORCE_WELL) {
-            mapc::well_step_kernel<<<(n_targets + 255) / 256, 256, 0, c->compute>>>(
+            const int per_block = mapc::kWellThreads * mapc::kWellBodies;
+            mapc::well_step_kernel<<<(n_targets + per_block - 1) / per_block, mapc::kWellThreads, 0, c->compute>>>(
                 c->posvelo[r], c->posvelo[b], c->packed[b], (int)c->i_first, n_targets, delta_time, damping);
             MAPC_CUDA(cudaGetLastError());
             ++c->launches;
@@ -1467,7 +1491,9 @@ mapc_status mapc_fp32_peak_probe(int device, int packed, float *tflops, float *m
 struct mapc_consumer {
     mapc_compute *producer = nullptr;
     int device = 0;
-    uint32_t n = 0;
+    uint32_t n = 0;                  // bodies this consumer sees: the producer's shard (all N when unsharded)
+    uint32_t first = 0;              // first body of that shard
+    bool async_mode = false;         // Render::m_asyncMode: same device, the producer's buffers are read in place
     cudaStream_t copy = nullptr;     // m_copyQueue
     cudaStream_t render = nullptr;   // m_commandQueue (direct queue): consumes the local buffer
     mapc::GatedStream gcopy, grender;  // the same streams behind the fence gate (fence.hpp)
@@ -1486,7 +1512,8 @@ struct mapc_consumer {
     uint64_t host_fence[2] = {0, 0};         // render fence value that marks host[i] complete
     uint32_t host_count[2] = {0, 0};
     uint64_t local_frame[2] = {0, 0};        // simulation step held by local[i]
-    uint64_t copies = 0;
+    uint64_t copies = 0;                     // frames handed out so far = simulation step of the next frame
+    uint64_t peer_copies = 0;                // cudaMemcpyPeerAsync calls issued by Draw (none in async mode)
 };
 
 // The producer is being destroyed first: finish what the consumer still has in flight against the
@@ -1499,7 +1526,8 @@ static void consumer_orphan(mapc_consumer *r)
     if (r->copy) cudaStreamSynchronize(r->copy);
     if (r->render) cudaStreamSynchronize(r->render);
     if (r->producer) {
-        if (r->producer->consumer_fence == r->copy_fence) r->producer->consumer_fence = nullptr;
+        if (r->producer->consumer_fence == r->copy_fence || r->producer->consumer_fence == r->render_fence)
+            r->producer->consumer_fence = nullptr;
         r->producer->consumer = nullptr;
     }
     r->producer = nullptr;
@@ -1517,7 +1545,8 @@ mapc_status mapc_consumer_destroy(mapc_consumer *r)
     if (r->copy) cudaStreamSynchronize(r->copy);
     if (r->render) cudaStreamSynchronize(r->render);
     if (r->producer) {
-        if (r->producer->consumer_fence == r->copy_fence) r->producer->consumer_fence = nullptr;
+        if (r->producer->consumer_fence == r->copy_fence || r->producer->consumer_fence == r->render_fence)
+            r->producer->consumer_fence = nullptr;
         if (r->producer->consumer == r) r->producer->consumer = nullptr;
     }
     for (int i = 0; i < 2; ++i) {
@@ -1551,10 +1580,19 @@ mapc_status mapc_consumer_wait_for_gpu(mapc_consumer *r)
 
 mapc_status mapc_consumer_create(mapc_consumer **out, mapc_compute *producer, int device)
 {
+    return mapc_consumer_create_ex(out, producer, device, 0u);
+}
+
+mapc_status mapc_consumer_create_ex(mapc_consumer **out, mapc_compute *producer, int device, uint32_t flags)
+{
     if (!out || !producer) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
     *out = nullptr;
-    if (producer->world != 1)
-        return fail(MAPC_ERR_UNSUPPORTED, "the headless consumer attaches to an unsharded Compute");
+    if (flags & ~(uint32_t)MAPC_CONSUMER_ASYNC) return fail(MAPC_ERR_INVALID_ARGUMENT, "unknown consumer flags 0x%x", flags);
+    const bool async_mode = (flags & MAPC_CONSUMER_ASYNC) != 0;
+    if (async_mode && device != producer->device)
+        // Particles::ShareHandles: asyncMode = (m_renderAdapterIndex == m_computeAdapterIndex), Particles.cpp:202
+        return fail(MAPC_ERR_INVALID_ARGUMENT, "an async consumer lives on its producer's device (%d), not %d",
+                    producer->device, device);
     if (!producer->has_state) return fail(MAPC_ERR_INVALID_ARGUMENT, "producer has no particle state");
     if (producer->consumer) return fail(MAPC_ERR_INVALID_ARGUMENT, "producer already has a consumer attached");
     int count = 0;
@@ -1566,7 +1604,9 @@ mapc_status mapc_consumer_create(mapc_consumer **out, mapc_compute *producer, in
     if (!r) return fail(MAPC_ERR_OUT_OF_MEMORY, "host allocation failed");
     r->producer = producer;
     r->device = device;
-    r->n = producer->n;
+    r->n = producer->n_local;          // a sharded producer hands out its own slice (each rank dumps its shard)
+    r->first = producer->i_first;
+    r->async_mode = async_mode;
     auto body = [&]() -> mapc_status {
         MAPC_CUDA(cudaStreamCreateWithFlags(&r->copy, cudaStreamNonBlocking));
         MAPC_CUDA(cudaStreamCreateWithFlags(&r->render, cudaStreamNonBlocking));
@@ -1574,24 +1614,29 @@ mapc_status mapc_consumer_create(mapc_consumer **out, mapc_compute *producer, in
         r->grender.stream = r->render;
         r->gcopy.device = r->grender.device = device;
         for (int i = 0; i < 2; ++i) {
-            MAPC_CUDA(cudaMalloc(&r->local[i], (size_t)r->n * sizeof(float4)));
+            // async mode has no local copies: the "draw" reads the producer's packed positions in place
+            if (!async_mode) MAPC_CUDA(cudaMalloc(&r->local[i], (size_t)r->n * sizeof(float4)));
             MAPC_CUDA(cudaHostAlloc(&r->host[i], (size_t)r->n * sizeof(float4), cudaHostAllocPortable));
         }
         MAPC_TRY(mapc_fence_create(&r->render_fence, 0));   // Render.cpp:588-595
         r->render_fence_value = 1;
         MAPC_TRY(mapc_fence_create(&r->copy_fence, 0));     // Render.cpp:611-617 (the shared one)
-        // Particles::ShareHandles, Particles.cpp:198-200
+        // Particles::ShareHandles, Particles.cpp:198-200; in async mode the fence the producer waits on is the
+        // RENDER fence (SetAsync(m_pRender->GetFence(), ...), Particles.cpp:205, Compute.cpp:961)
         mapc_shared_handles sh;
-        MAPC_TRY(mapc_compute_shared_handles(producer, r->copy_fence, &sh));
+        MAPC_TRY(mapc_compute_shared_handles(producer, async_mode ? r->render_fence : r->copy_fence, &sh));
         r->shared_buffer_index = sh.buffer_index;           // Render.cpp:224
         r->compute_fence = sh.fence;
         // "copy initial state from the other adapter" (Render.cpp:253-): both local buffers
         const uint32_t newest = 1u - sh.buffer_index;
-        for (int i = 0; i < 2; ++i)
-            MAPC_CUDA(cudaMemcpyPeerAsync(r->local[i], device, producer->packed[newest], producer->device,
-                                          (size_t)r->n * sizeof(float4), r->copy));
-        MAPC_CUDA(cudaMemcpyAsync(r->host[0], r->local[0], (size_t)r->n * sizeof(float4),
-                                  cudaMemcpyDeviceToHost, r->copy));
+        const float4 *src = producer->packed[newest] + r->first;
+        if (!async_mode) {
+            for (int i = 0; i < 2; ++i)
+                MAPC_CUDA(cudaMemcpyPeerAsync(r->local[i], device, src, producer->device, (size_t)r->n * sizeof(float4), r->copy));
+            MAPC_CUDA(cudaMemcpyAsync(r->host[0], r->local[0], (size_t)r->n * sizeof(float4), cudaMemcpyDeviceToHost, r->copy));
+        } else {
+            MAPC_CUDA(cudaMemcpyAsync(r->host[0], src, (size_t)r->n * sizeof(float4), cudaMemcpyDeviceToHost, r->copy));
+        }
         r->host_count[0] = r->n;
         return mapc_consumer_wait_for_gpu(r);
     };
@@ -1607,16 +1652,60 @@ mapc_status mapc_consumer_create(mapc_consumer **out, mapc_compute *producer, in
     return MAPC_OK;
 }
 
+// The async frame (Render::Draw with m_asyncMode, Render.cpp:849-852 and :928-932): producer and consumer share
+// a device, so there is no copy queue and no local buffer -- the render stream waits for the PREVIOUS Simulate
+// (compute fence F-1), consumes the side that Simulate wrote where it lies, then waits for the upcoming
+// Simulate (compute fence F) before it signals the render fence; the value handed back is the RENDER fence
+// value, which is the fence Compute::Simulate waits on in this mode (Compute.cpp:961, :1012).
+static mapc_status consumer_draw_async(mapc_consumer *r, int n_draw, uint64_t *inout_fence_value)
+{
+    const uint64_t compute_fence_value = *inout_fence_value;
+    MAPC_TRY(mapc::gs_wait(&r->grender, r->compute_fence, compute_fence_value - 1));        // Render.cpp:851
+    const uint32_t src_side = 1u - r->shared_buffer_index;   // the side the previous Simulate wrote
+    r->shared_buffer_index = 1u - r->shared_buffer_index;
+    const uint32_t slot = r->frame_index;
+    if (n_draw > 0) {
+        float4 *dst = r->host[slot];
+        const float4 *src = r->producer->packed[src_side] + r->first;
+        const size_t bytes = (size_t)n_draw * sizeof(float4);
+        cudaStream_t render = r->render;
+        MAPC_TRY(mapc::gs_call(&r->grender, [=]() -> mapc_status {
+            MAPC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, render));
+            return MAPC_OK;
+        }));
+    }
+    r->host_frame[slot] = r->copies++;       // simulation step shown (0 = the initial state)
+    r->host_count[slot] = (uint32_t)n_draw;
+    // the next frame must not start before THIS frame's Simulate has produced its results (:930); the value
+    // belongs to the Simulate submitted after this call, so the render stream gates here (fence.hpp)
+    MAPC_TRY(mapc::gs_wait(&r->grender, r->compute_fence, compute_fence_value));
+    *inout_fence_value = r->render_fence_value;                                              // :931
+    return MAPC_OK;
+}
+
 mapc_status mapc_consumer_draw(mapc_consumer *r, int num_active_particles, uint64_t *inout_fence_value,
                                int num_particles_copied)
 {
     NvtxRange range("mapc: consumer Draw");
     if (!r || !inout_fence_value) return fail(MAPC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!r->producer) return fail(MAPC_ERR_INVALID_ARGUMENT, "the producer of this consumer has been destroyed");
-    if (num_active_particles < 0 || (uint32_t)num_active_particles > r->n || num_particles_copied < 0 ||
-        (uint32_t)num_particles_copied > r->n)
-        return fail(MAPC_ERR_INVALID_ARGUMENT, "particle counts outside [0, %u]", r->n);
+    const uint32_t n_global = r->producer->n;
+    if (num_active_particles < 0 || (uint32_t)num_active_particles > n_global || num_particles_copied < 0 ||
+        (uint32_t)num_particles_copied > n_global)
+        return fail(MAPC_ERR_INVALID_ARGUMENT, "particle counts outside [0, %u]", n_global);
+    // counts are global (the reference's sliders, Particles.cpp:380-394); a shard takes its part of them
+    auto in_shard = [&](int count) -> int {
+        long long c = (long long)count - (long long)r->first;
+        if (c < 0) c = 0;
+        if (c > (long long)r->n) c = r->n;
+        return (int)c;
+    };
+    num_active_particles = in_shard(num_active_particles);
+    num_particles_copied = in_shard(num_particles_copied);
     DeviceGuard g(r->device);
+    if (r->async_mode) {
+        MAPC_TRY(consumer_draw_async(r, num_active_particles, inout_fence_value));
+    } else {
     const uint64_t compute_fence_value = *inout_fence_value;
 
     // ---- CopySimulationResults(in_fenceValue, in_numParticlesCopied), Render.cpp:789-831 ---------
@@ -1627,7 +1716,7 @@ mapc_status mapc_consumer_draw(mapc_consumer *r, int num_active_particles, uint6
     r->shared_buffer_index = 1u - r->shared_buffer_index;      // :800
     if (num_particles_copied > 0) {                            // :814 copy just the particles required
         float4 *dst = r->local[dst_local];
-        const float4 *src = r->producer->packed[src_shared];
+        const float4 *src = r->producer->packed[src_shared] + r->first;
         const int dst_dev = r->device, src_dev = r->producer->device;
         const size_t bytes = (size_t)num_particles_copied * sizeof(float4);
         cudaStream_t copy = r->copy;
@@ -1635,6 +1724,7 @@ mapc_status mapc_consumer_draw(mapc_consumer *r, int num_active_particles, uint6
             MAPC_CUDA(cudaMemcpyPeerAsync(dst, dst_dev, src, src_dev, bytes, copy));
             return MAPC_OK;
         }));
+        r->peer_copies++;
     }
     r->local_frame[dst_local] = r->copies++;   // results of the PREVIOUS Simulate (step number = copies so far)
     // don't start the next copy until the compute device has produced new results (:826).  The value
@@ -1663,8 +1753,10 @@ mapc_status mapc_consumer_draw(mapc_consumer *r, int num_active_particles, uint6
     // render waits for this frame's copy; hand the copy fence value to the producer (:925-926)
     MAPC_TRY(mapc::gs_wait(&r->grender, r->copy_fence, r->copy_fence_value));
     *inout_fence_value = r->copy_fence_value;
+    }
 
     // ---- MoveToNextFrame, Render.cpp:653-677 ---------------------------------------------------------
+    const uint32_t slot = r->frame_index;
     r->frame_fence_values[r->frame_index] = r->render_fence_value;
     r->host_fence[slot] = r->render_fence_value;
     MAPC_TRY(mapc::gs_signal(&r->grender, r->render_fence, r->render_fence_value));
@@ -1694,7 +1786,7 @@ mapc_status mapc_consumer_counters(const mapc_consumer *r, uint64_t out[8])
     out[4] = r->shared_buffer_index;
     out[5] = r->current_buffer_index;
     out[6] = r->frames_drawn;
-    out[7] = r->copies;
+    out[7] = r->peer_copies;
     return MAPC_OK;
 }
 

@@ -608,31 +608,66 @@ integrate_kernel(const mapc_posvelo *__restrict__ in, mapc_posvelo *__restrict__
 }
 
 // The step the reference actually dispatches (nBodyGravityCS.hlsl:86-109): one gravity well at
-// the origin, note invDist = -1/sqrt (:97).  ~25 flop against 64 B of traffic per body: HBM-bound.
-__global__ void __launch_bounds__(256)
+// the origin, note invDist = -1/sqrt (:97).  ~25 flop against 80 B of traffic per body (32 B PosVelo in,
+// 32 B out, 16 B packed mirror): HBM-bound, so the shape is the one of a streaming copy -- B bodies per
+// thread with all their loads issued before the first use (2B independent 16-byte loads in flight per
+// thread), consecutive threads on consecutive bodies, streaming (evict-first) loads and stores because
+// nothing is read twice inside a step.  kWellBodies bodies per thread, kWellThreads threads per block.
+constexpr int kWellBodies = 2;
+constexpr int kWellThreads = 256;
+
+#ifdef MAPC_HOST_EMULATION
+static inline float4 ld_stream(const float4 *p) { return *p; }
+static inline void st_stream(float4 *p, float4 v) { *p = v; }
+#else
+__device__ __forceinline__ float4 ld_stream(const float4 *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float4 *p, float4 v) { __stcs(p, v); }
+#endif
+
+__global__ void __launch_bounds__(kWellThreads)
 well_step_kernel(const mapc_posvelo *__restrict__ in, mapc_posvelo *__restrict__ out,
                  float4 *__restrict__ pos_next, int i_first, int n_targets, float dt, float damping)
 {
+    const int base = blockIdx.x * (kWellThreads * kWellBodies) + threadIdx.x;
+    float4 pos_in[kWellBodies], vel_in[kWellBodies];
+#pragma unroll
+    for (int k = 0; k < kWellBodies; ++k) {
+        const int i = base + k * kWellThreads;
+        if (i < n_targets) {
+            const float4 *src = reinterpret_cast<const float4 *>(in + i);
+            pos_in[k] = ld_stream(src);
+            vel_in[k] = ld_stream(src + 1);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kWellBodies; ++k) {
+        const int i = base + k * kWellThreads;
+        if (i >= n_targets) continue;
+        const float4 p = pos_in[k];
+        float d2 = __fmaf_rn(p.x, p.x, MAPC_SOFTENING_SQUARED);
+        d2 = __fmaf_rn(p.y, p.y, d2);
+        d2 = __fmaf_rn(p.z, p.z, d2);
+        const float inv = -rsqrt_approx(d2);
+        const float inv3 = __fmul_rn(__fmul_rn(inv, inv), inv);
+        const float s = __fmul_rn(inv3, MAPC_PARTICLE_MASS);
+        const float ax = __fmul_rn(p.x, s);
+        const float ay = __fmul_rn(p.y, s);
+        const float az = __fmul_rn(p.z, s);
+        float4 pos_out, vel_out;
+        integrate_body(p, vel_in[k], ax, ay, az, dt, damping, pos_out, vel_out);
+        float4 *dst = reinterpret_cast<float4 *>(out + i);
+        st_stream(dst, pos_out);
+        st_stream(dst + 1, vel_out);
+        st_stream(pos_next + i_first + i, pos_out);
+    }
+}
+
+// packed float4 position mirror from a PosVelo array (after upload / state copy)
+__global__ void __launch_bounds__(256)
+pack_positions_kernel(const mapc_posvelo *__restrict__ in, float4 *__restrict__ pos, int n)
+{
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_targets) return;
-    const float4 *src = reinterpret_cast<const float4 *>(in + i);
-    const float4 pos_in = src[0];
-    const float4 vel_in = src[1];
-    float d2 = __fmaf_rn(pos_in.x, pos_in.x, MAPC_SOFTENING_SQUARED);
-    d2 = __fmaf_rn(pos_in.y, pos_in.y, d2);
-    d2 = __fmaf_rn(pos_in.z, pos_in.z, d2);
-    const float inv = -rsqrt_approx(d2);
-    const float inv3 = __fmul_rn(__fmul_rn(inv, inv), inv);
-    const float s = __fmul_rn(inv3, MAPC_PARTICLE_MASS);
-    const float ax = __fmul_rn(pos_in.x, s);
-    const float ay = __fmul_rn(pos_in.y, s);
-    const float az = __fmul_rn(pos_in.z, s);
-    float4 pos_out, vel_out;
-    integrate_body(pos_in, vel_in, ax, ay, az, dt, damping, pos_out, vel_out);
-    float4 *dst = reinterpret_cast<float4 *>(out + i);
-    dst[0] = pos_out;
-    dst[1] = vel_out;
-    pos_next[i_first + i] = pos_out;
+    if (i < n) pos[i] = reinterpret_cast<const float4 *>(in + i)[0];
 }
 
 // ---- initial conditions: InitializeParticles / LoadParticles, USE_SCALAR_OPTIMIZED branch ---------------------
@@ -712,14 +747,6 @@ init_particles_kernel(mapc_posvelo *__restrict__ side_a, mapc_posvelo *__restric
         a[0] = pos; a[1] = vel;
         b[0] = pos; b[1] = vel;
     }
-}
-
-// packed float4 position mirror from a PosVelo array (after upload / state copy)
-__global__ void __launch_bounds__(256)
-pack_positions_kernel(const mapc_posvelo *__restrict__ in, float4 *__restrict__ pos, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) pos[i] = reinterpret_cast<const float4 *>(in + i)[0];
 }
 
 // FP32 roofline probe: 16 independent accumulator chains per thread, nothing but FMAs.

@@ -235,7 +235,8 @@ int emu_step_well(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next_out
     const mapc_posvelo *pin = reinterpret_cast<const mapc_posvelo *>(in_local.data());
     mapc_posvelo *pout = reinterpret_cast<mapc_posvelo *>(out_local.data());
     if (n_targets > 0)
-        cuda_emu::launch(dim3((n_targets + 255) / 256), dim3(256), 0, [&] {
+        cuda_emu::launch(dim3((n_targets + mapc::kWellThreads * mapc::kWellBodies - 1) / (mapc::kWellThreads * mapc::kWellBodies)),
+                         dim3(mapc::kWellThreads), 0, [&] {
             mapc::well_step_kernel(pin, pout, pos_next.data(), i_first, n_targets, dt, damping);
         });
     std::vector<PV> all(n);

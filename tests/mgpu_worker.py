@@ -80,6 +80,42 @@ def main():
                 print(f"n={n} world={world} steps={args.steps} exchange={mode} bit-identical={bool(flag.item())} "
                       f"sha256[:16]={digest}", flush=True)
             ok = ok and bool(flag.item())
+    # ---- sharded extras: device-side initial conditions, and a headless consumer per rank ------------------
+    n = 16_384
+    if n % world == 0:
+        first, count = pkg.dist.shard_range(n, rank, world)
+        with pkg.Compute(n, local_rank) as s:
+            s.InitializeParticles(seed=5)
+            ic_full = s.Download()
+            frames_ref = [ic_full["pos"].copy()]
+            for _ in range(4):
+                s.Simulate(n, 0)
+                s.WaitForGpu()
+                frames_ref.append(s.Download()["pos"].copy())
+        for async_mode in (False, True):
+            nid = pkg.dist.broadcast_bytes(pkg.nccl_unique_id() if rank == 0 else None, pkg.NCCL_UNIQUE_ID_BYTES, 0, dev)
+            with pkg.Compute(n, local_rank, rank=rank, world=world, nccl_id=nid) as c:
+                c.InitializeParticles(seed=5)            # every rank generates its shard + all positions on its GPU
+                same_ic = c.Download().tobytes() == ic_full[first:first + count].tobytes()
+                dist.barrier()
+                same_frames = True
+                with pkg.Consumer(c, local_rank, async_mode=async_mode) as r:   # each rank dumps its own slice
+                    for _ in range(4):
+                        fence = c.GetFenceValue()
+                        fence = r.Draw(n, fence, n)
+                        c.Simulate(n, fence)
+                        r.WaitForGpu()
+                        frame, pos = r.Latest()
+                        same_frames = same_frames and pos.shape[0] == count and \
+                            pos.tobytes() == frames_ref[frame][first:first + count].tobytes()
+                    c.WaitForGpu()
+                dist.barrier()
+            flag = torch.tensor([1 if (same_ic and same_frames) else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print(f"n={n} world={world} sharded InitializeParticles + {'async' if async_mode else 'copying'} consumer "
+                      f"per rank bit-identical={bool(flag.item())}", flush=True)
+            ok = ok and bool(flag.item())
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -303,20 +303,102 @@ def test_gpu_timer_and_launch_counter(mapc, gpu):
         assert abs(stamped - events) <= 0.15 * events + 0.004, (stamped, events)
 
 
-def test_init_particles_two_shells(mapc, gpu):
-    n = 4096
-    with mapc.Compute(n, 0) as c:
-        c.InitializeParticles(seed=42)
-        p = c.Download()
-    half = n // 2
-    for sl, cx in ((slice(0, half), 300.0), (slice(half, n), -300.0)):
+def test_init_particles_equals_oracle_restatement(mapc, oracle, gpu):
+    """InitializeParticles on the device (init_particles_kernel: the reference's two shells of radius 400 at
+    x = +-300 with tangential speed <= 15, Compute.cpp:719-749 / :820-844, one seeded LCG stream per particle)
+    against the oracle's restatement of the same generator: every byte, both ping-pong sides, odd N too."""
+    for n, seed in ((4096, 42), (1001, 7), (262_144, 1)):
+        ref = oracle.init_particles(n, seed)
+        with mapc.Compute(n, 0) as c:
+            c.InitializeParticles(seed=seed)
+            p = c.Download()
+            assert p.tobytes() == ref.tobytes(), (n, seed)
+            c.Simulate(0, 0)                       # flips the ping-pong without touching anything
+            c.WaitForGpu()
+            assert c.Download().tobytes() == ref.tobytes()      # the other side was initialised alike
+            # and the packed mirror feeds the force loop: one well step equals the oracle's on the same state
+            c.SetForceMode(mapc.FORCE_WELL)
+            c.Simulate(n, 0)
+            c.WaitForGpu()
+            err = oracle.rel_errors(c.Download(), oracle.step_well(ref))
+            assert max(err.values()) <= 2e-6, err
+    half = 2048
+    p = oracle.init_particles(4096, 42)
+    for sl, cx in ((slice(0, half), 300.0), (slice(half, 4096), -300.0)):
         d = p["pos"][sl, :3] - np.array([cx, 0, 0], dtype=np.float32)
         np.testing.assert_allclose(np.linalg.norm(d, axis=1), 400.0, rtol=1e-5)
-    speed = np.linalg.norm(p["velo"][:, :3], axis=1)
-    assert speed.max() <= 15.0 * (1 + 1e-5) and speed.mean() > 5.0
     # velocity is tangential: perpendicular to the direction to the origin
     dots = np.einsum("ij,ij->i", p["velo"][:, :3], p["pos"][:, :3])
     assert np.abs(dots).max() < 1e-2 * 15.0 * 700.0
+
+
+def test_async_consumer_reads_in_place_and_shows_the_same_frames(mapc, oracle, gpu):
+    """The reference's async mode (consumer on the producer's device: Particles.cpp:202-207, Render.cpp:849-852,
+    :928-932): no copy stream, no local buffers, the producer's packed positions are dumped in place after
+    waiting for compute fence F-1, and the RENDER fence value gates the next Simulate.  Frames must equal the
+    copying consumer's bit for bit (same steps, same bytes), arrive one step earlier, and no device-to-device
+    copy may be issued."""
+    n, frames = 4096, 7
+    p = gentle_sphere(mapc, n, seed=4, speed=2.0)
+
+    def run(async_mode):
+        seen, latency = {}, []
+        with mapc.Compute(n, 0) as c:
+            c.Upload(p)
+            with mapc.Consumer(c, 0, async_mode=async_mode) as r:
+                f0, pos0 = r.Latest()
+                assert f0 == 0 and pos0.tobytes() == p["pos"].tobytes()
+                for k in range(frames):
+                    fence = c.GetFenceValue()
+                    fence = r.Draw(n, fence, n)
+                    c.Simulate(n, fence)
+                    r.WaitForGpu()
+                    frame, pos = r.Latest()
+                    seen[frame] = pos
+                    latency.append(k - frame)
+                c.WaitForGpu()
+                counters = r.Counters()
+                final = c.Download()
+        return seen, latency, counters, final
+
+    copy_seen, copy_lat, copy_cnt, copy_final = run(False)
+    async_seen, async_lat, async_cnt, async_final = run(True)
+    assert async_final.tobytes() == copy_final.tobytes()            # the trajectory does not depend on the consumer
+    assert async_cnt["copies"] == 0 and copy_cnt["copies"] == frames
+    common = sorted(set(copy_seen) & set(async_seen))
+    assert len(common) >= frames - 2
+    for frame in common:
+        assert async_seen[frame].tobytes() == copy_seen[frame].tobytes(), frame
+    # Draw k (0-based) of the async consumer dumps the result of step k (the previous Simulate): frame == k;
+    # the copying consumer is one buffer hop behind
+    assert async_lat == [0] * frames, async_lat
+    assert copy_lat[1:] == [1] * (frames - 1), copy_lat
+    states = [p]
+    for _ in range(frames):
+        states.append(oracle.step_allpairs(states[-1], flavour=oracle.MIRRORED))
+    for frame, pos in async_seen.items():
+        ref = states[frame]["pos"]
+        assert np.abs(pos[:, :3] - ref[:, :3]).max() / np.abs(ref[:, :3]).max() <= TOL_10, frame
+
+
+def test_async_consumer_gates_the_producer_on_the_render_fence(mapc, gpu):
+    """In async mode Simulate(F) waits for render fence F-1 (Compute.cpp:1012 with the fence SetAsync installed,
+    :961): two Simulates in a row without a Draw in between must be refused or gated, never run ahead."""
+    n = 2048
+    p = gentle_sphere(mapc, n, seed=9)
+    with mapc.Compute(n, 0) as c:
+        c.Upload(p)
+        with pytest.raises(mapc.MapcError):
+            mapc.Consumer(c, 99, async_mode=True)          # an async consumer lives on the producer's device
+        with mapc.Consumer(c, 0, async_mode=True) as r:
+            for _ in range(3):
+                f = c.GetFenceValue()
+                out = r.Draw(n, f, n)
+                c.Simulate(n, out)
+            c.WaitForGpu()
+            r.WaitForGpu()
+            cnt = r.Counters()
+            assert cnt["frames_drawn"] == 3 and cnt["render_fence_completed"] >= cnt["render_fence_value"] - 1
 
 
 def test_full_size_262144_properties_and_subsampled_parity(mapc, oracle, gpu):
