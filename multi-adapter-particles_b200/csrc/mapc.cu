@@ -392,6 +392,7 @@ struct Switches {
     bool tma;           // MAPC_TMA=1: cp.async.bulk source staging instead of LDG/STS
     bool shfl;          // MAPC_SHFL=1: warp-shuffle broadcast of staged sources instead of LDS broadcast
     bool ring;          // MAPC_RING=0: every target block its own scratch slot (no L2-resident ring)
+    int wait_timeout_ms;  // MAPC_WAIT_TIMEOUT_MS: bound of every in-kernel wait (peer step flag, ring slot)
     bool mass_in_loop;  // MAPC_MASS_IN_LOOP=1: 12-op pair with the shader's per-pair mass multiply
     bool timers;        // MAPC_TIMERS=0: no "simulate ms" timer at all
     bool timer_events;  // MAPC_TIMER_EVENTS=1: cudaEvent pairs instead of in-kernel stamps
@@ -409,6 +410,7 @@ Switches read_switches()
     w.tma = env_int("MAPC_TMA", 0) != 0;
     w.shfl = env_int("MAPC_SHFL", 0) != 0;
     w.ring = env_int("MAPC_RING", 1) != 0;
+    w.wait_timeout_ms = env_int("MAPC_WAIT_TIMEOUT_MS", 20000);
     w.mass_in_loop = env_int("MAPC_MASS_IN_LOOP", 0) != 0;
     w.timers = env_int("MAPC_TIMERS", 1) != 0;
     w.timer_events = env_int("MAPC_TIMER_EVENTS", 0) != 0;
@@ -483,6 +485,7 @@ struct mapc_compute {
     uint64_t t_fence_value[kTimerSlots] = {};  // fence value signalled after the slot's step(s)
     unsigned long long *stamps = nullptr;      // pinned host: [slot][begin, end] in ns
     unsigned *done = nullptr;                  // device: [0] target blocks integrated this step, [1] cell ticket
+    unsigned long long *error_word = nullptr;  // pinned host: [0] != 0 after an in-kernel wait timed out, [1] detail
     unsigned long long *stamp_begin_next = nullptr, *stamp_end_next = nullptr;  // for the next force launch(es)
     unsigned long long fence_write_next = 0;   // != 0: the step's last block writes this value to the fence word
     uint64_t t_next = 0, t_resolved = 0;
@@ -676,6 +679,9 @@ mapc_status create_common(mapc_compute **out, uint32_t n, int device, int rank, 
         memset(c->stamps, 0, 2 * mapc_compute::kTimerSlots * sizeof(unsigned long long));
         MAPC_CUDA(cudaMalloc(&c->done, 64));
         MAPC_CUDA(cudaMemset(c->done, 0, 64));
+        MAPC_CUDA(cudaHostAlloc((void **)&c->error_word, 2 * sizeof(unsigned long long),
+                                cudaHostAllocPortable | cudaHostAllocMapped));
+        c->error_word[0] = c->error_word[1] = 0;
         MAPC_CUDA(cudaMalloc(&c->counters, ((size_t)c->n_local / 64 + 2) * sizeof(unsigned)));
         MAPC_CUDA(cudaMemset(c->counters, 0, ((size_t)c->n_local / 64 + 2) * sizeof(unsigned)));
         // Compute.cpp:434-436: fence created with value 0, m_fenceValue++ -> 1
@@ -887,6 +893,7 @@ mapc_status mapc_compute_destroy(mapc_compute *c)
     if (c->counters) cudaFree(c->counters);
     if (c->done) cudaFree(c->done);
     if (c->stamps) cudaFreeHost(c->stamps);
+    if (c->error_word) cudaFreeHost(c->error_word);
     if (c->ev_integrated) cudaEventDestroy(c->ev_integrated);
     for (int k = 0; k < mapc_compute::kTimerSlots; ++k) {
         if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]);
@@ -1081,6 +1088,8 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             args.dt = delta_time;
             args.damping = damping;
             args.done = c->done;
+            args.error_word = c->error_word;
+            args.wait_timeout_ns = (unsigned long long)sw.wait_timeout_ms * 1000000ull;
             args.stamp_begin = c->stamp_begin_next;   // consumed by the first launch of the step
             args.stamp_end = c->stamp_end_next;       // every launch: whichever finishes the step writes it
             args.fence_word = c->fence_write_next ? (unsigned long long *)c->fence->word : nullptr;
@@ -1261,6 +1270,13 @@ mapc_status mapc_compute_wait_for_gpu(mapc_compute *c)
         if (q != ncclSuccess || (async != ncclSuccess && async != ncclInProgress))
             return fail(MAPC_ERR_NCCL, "NCCL communicator reports an asynchronous error: %s",
                         g_nccl.GetErrorString(q != ncclSuccess ? q : async));
+    }
+    if (c->error_word && c->error_word[0] != 0) {
+        const unsigned long long kind = c->error_word[0], detail = c->error_word[1];
+        c->error_word[0] = c->error_word[1] = 0;
+        return fail(MAPC_ERR_TIMEOUT, kind == 1 ? "a force cell gave up waiting for a peer rank to publish step %llu: "
+                    "the step's results are invalid" : "a force cell gave up waiting for scratch-ring slot of target block "
+                    "%llu: the step's results are invalid", detail);
     }
     if (mapc_fence_completed_value(c->fence) < v)
         return fail(MAPC_ERR_CUDA, "fence at %llu after drain, expected >= %llu",

@@ -199,6 +199,12 @@ struct StepArgs {
     unsigned long long *stamp_begin;   // pinned host memory, or null
     unsigned long long *stamp_end;     // pinned host memory, or null
     unsigned *done;                    // target blocks integrated so far this step (device); never null for FUSE
+    // Every in-kernel wait (a peer's step flag, a scratch-ring slot) is bounded: after wait_timeout_ns the
+    // waiting block stores MAPC_ERR_TIMEOUT-style evidence to error_word (pinned host memory: [0] = 1 peer
+    // flag / 2 ring slot, [1] = what it waited for) and carries on, so the grid always terminates and
+    // WaitForGpu reports the step as failed instead of the GPU hanging.
+    unsigned long long wait_timeout_ns;
+    unsigned long long *error_word;
     // fence signal from inside the kernel (ID3D12CommandQueue::Signal after the Dispatch, Compute.cpp:999):
     // the same last block stores fence_value to the fence word (pinned host memory) -- or null
     unsigned long long *fence_word;
@@ -336,8 +342,18 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
     if (PEER) {
         const unsigned long long *flag = a.seg_flag[kseg];
         if (flag != nullptr) {
-            if (tid == 0)
-                while (load_acquire_sys(flag) < a.flag_expect) __nanosleep(200);
+            if (tid == 0) {
+                const unsigned long long t0 = global_timer_ns();
+                while (load_acquire_sys(flag) < a.flag_expect) {
+                    __nanosleep(200);
+                    if (a.error_word != nullptr && global_timer_ns() - t0 > a.wait_timeout_ns) {
+                        a.error_word[1] = a.flag_expect;
+                        a.error_word[0] = 1ull;     // a peer never published this step
+                        __threadfence_system();
+                        break;
+                    }
+                }
+            }
             __syncthreads();
         }
     }
@@ -494,7 +510,16 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
         if (a.slot_gen != nullptr) {
             if (tid == 0) {
                 const unsigned want = (unsigned)(ib / a.scratch_blocks);
-                while (load_acquire_gpu(a.slot_gen + slot) != want) __nanosleep(100);
+                const unsigned long long t0 = global_timer_ns();
+                while (load_acquire_gpu(a.slot_gen + slot) != want) {
+                    __nanosleep(100);
+                    if (a.error_word != nullptr && global_timer_ns() - t0 > a.wait_timeout_ns) {
+                        a.error_word[1] = (unsigned long long)ib;
+                        a.error_word[0] = 2ull;     // a scratch-ring slot was never released
+                        __threadfence_system();
+                        break;
+                    }
+                }
             }
             __syncthreads();
         }

@@ -53,6 +53,16 @@ def main():
     b_in = pkg.ic.plummer(1111, 300.0, seed=33, velocity_scale=0.1)
     S_b = orc.default_segments(b_in.shape[0])
     b_out = ref.step_allpairs(b_in, S_b, dt=0.05, damping=0.995)
+    # a size at which the chains of the canonical order matter: N = 98,304 -> 32 segments of 3,072 sources = one
+    # 2,048-source chain + one of 1,024, folded left to right.  The input is regenerated from its seed (its
+    # sha256 is stored); outputs are kept for 384 targets only.
+    import hashlib
+    c_n, c_radius, c_seed = 98_304, 5800.0, 34
+    c_in = pkg.ic.uniform_sphere(c_n, c_radius, c_seed, speed=1.0)
+    c_idx = np.sort(rng.choice(c_n, 384, replace=False)).astype(np.int32)
+    S_c = orc.default_segments(c_n)
+    c_out = ref.step_allpairs_targets(c_in, c_idx, S_c, dt=0.1, damping=1.0, chain=orc.default_chain())
+    assert c_out.tobytes() != ref.step_allpairs_targets(c_in, c_idx, S_c, dt=0.1, damping=1.0, chain=0).tobytes()
     soft, pmass = ref.constants()
     np.savez_compressed(os.path.join(HERE, "ref_shader_vectors.npz"),
                         pair_ai=ai, pair_bj=bj, pair_bi=bi, pair_mass=mass, pair_particles=particles,
@@ -60,6 +70,10 @@ def main():
                         well_in=f32(w), well_out_a=f32(well_a), well_out_b=f32(well_b),
                         allpairs_a_in=f32(a_in), allpairs_a_out=f32(a_out), allpairs_a_S=S_a,
                         allpairs_b_in=f32(b_in), allpairs_b_out=f32(b_out), allpairs_b_S=S_b,
+                        allpairs_c_n=c_n, allpairs_c_radius=np.float64(c_radius), allpairs_c_seed=c_seed,
+                        allpairs_c_sha256=np.frombuffer(hashlib.sha256(c_in.tobytes()).digest(), dtype=np.uint8),
+                        allpairs_c_targets=c_idx, allpairs_c_out=f32(c_out), allpairs_c_S=S_c,
+                        allpairs_c_chain=orc.default_chain(),
                         softening_squared=np.float32(soft), particle_mass=np.float32(pmass))
     print("wrote ref_shader_vectors.npz")
 

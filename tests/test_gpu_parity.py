@@ -111,6 +111,14 @@ def test_against_reference_shader_vectors(mapc, oracle, gpu):
         assert int(g[f"allpairs_{case}_S"]) == mapc.plan_segments(inp.shape[0])
         got = gpu_steps(mapc, inp, 1, dt=dt, damping=damping)
         assert_close(oracle, got, g[f"allpairs_{case}_out"], TOL_1, f"reference shader all-pairs {case}")
+    # segments longer than a chain (N = 98,304: 2,048 + 1,024 sources per segment), 384 targets kept
+    import hashlib
+    n, radius, seed = int(g["allpairs_c_n"]), float(g["allpairs_c_radius"]), int(g["allpairs_c_seed"])
+    p = mapc.ic.uniform_sphere(n, radius, seed, speed=1.0)
+    assert hashlib.sha256(p.tobytes()).digest() == g["allpairs_c_sha256"].tobytes()
+    assert int(g["allpairs_c_chain"]) == mapc.plan_chain_sources()
+    got = gpu_steps(mapc, p, 1)
+    assert_close(oracle, got[g["allpairs_c_targets"]], g["allpairs_c_out"], TOL_1, "reference shader all-pairs, chained")
     w = g["well_in"].view(mapc.POSVELO_DTYPE).reshape(-1)
     assert_close(oracle, gpu_steps(mapc, w, 1, mode=mapc.FORCE_WELL), g["well_out_a"], 2e-6, "reference CSMain")
     assert_close(oracle, gpu_steps(mapc, w, 1, dt=0.05, damping=0.995, mode=mapc.FORCE_WELL), g["well_out_b"],

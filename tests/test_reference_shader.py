@@ -64,6 +64,29 @@ def test_oracle_allpairs_equals_reference_vectors(mapc, oracle, vec, case, dt, d
     assert scalar.tobytes() == vector.tobytes()
 
 
+def chained_case(mapc, vec):
+    """the N = 98,304 case of the fixture: input regenerated from its seed and checked against the stored hash"""
+    import hashlib
+    n, radius, seed = int(vec["allpairs_c_n"]), float(vec["allpairs_c_radius"]), int(vec["allpairs_c_seed"])
+    p = mapc.ic.uniform_sphere(n, radius, seed, speed=1.0)
+    assert hashlib.sha256(p.tobytes()).digest() == vec["allpairs_c_sha256"].tobytes()
+    return p, vec["allpairs_c_targets"], int(vec["allpairs_c_S"]), int(vec["allpairs_c_chain"])
+
+
+def test_oracle_chained_order_equals_reference_vectors(mapc, oracle, vec):
+    """Segments longer than a chain (3,072 sources = a 2,048-source chain + one of 1,024): the oracle's
+    canonical order against the reference's bodyBodyInteraction driven in that order."""
+    p, idx, S, chain = chained_case(mapc, vec)
+    assert S == oracle.default_segments(p.shape[0]) and chain == oracle.default_chain()
+    got = oracle.step_allpairs_targets(p, idx, flavour=oracle.LITERAL)
+    assert got.view(np.float32).tobytes() == vec["allpairs_c_out"].tobytes()
+    one_chain = oracle.step_allpairs_targets(p, idx, flavour=oracle.LITERAL, chunk=0)
+    assert one_chain.tobytes() != got.tobytes()
+    scalar = oracle.accel_allpairs(p, flavour=oracle.LITERAL, targets=idx[:16], scalar=True)
+    vector = oracle.accel_allpairs(p, flavour=oracle.LITERAL, targets=idx[:16])
+    assert scalar.tobytes() == vector.tobytes()
+
+
 # ---- the live library ----------------------------------------------------------------------------
 def test_vectors_are_what_the_library_produces(mapc, ref, vec):
     """the committed fixture is not stale"""
@@ -72,6 +95,9 @@ def test_vectors_are_what_the_library_produces(mapc, ref, vec):
     inp = pv(mapc, vec["allpairs_b_in"])
     out = ref.step_allpairs(inp, int(vec["allpairs_b_S"]), dt=0.05, damping=0.995)
     assert out.tobytes() == vec["allpairs_b_out"].tobytes()
+    p, idx, S, chain = chained_case(mapc, vec)
+    out = ref.step_allpairs_targets(p, idx[:64], S, chain=chain)
+    assert out.view(np.float32).tobytes() == vec["allpairs_c_out"][:64].tobytes()
 
 
 @pytest.mark.parametrize("n,ic", [(64, "sphere"), (100, "sphere"), (1000, "plummer"), (4097, "sphere"),
@@ -89,6 +115,18 @@ def test_oracle_equals_live_reference(mapc, oracle, ref, n, ic):
     targets = np.array([0, n // 3, n - 1], dtype=np.int32)
     assert (ref.step_allpairs_targets(p, targets, S, n_sources=n - n // 4).tobytes() ==
             oracle.step_allpairs_targets(p, targets, n_sources=n - n // 4, S=S, flavour=oracle.LITERAL).tobytes())
+
+
+def test_oracle_equals_live_reference_with_chains(mapc, oracle, ref):
+    """N = 70,001 (ragged last tile): 32 segments of ~2,188 sources = a full 2,048-source chain + a short one."""
+    n = 70_001
+    p = mapc.ic.uniform_sphere(n, 5000.0, seed=77, speed=1.0)
+    targets = np.sort(np.random.default_rng(3).choice(n, 96, replace=False)).astype(np.int32)
+    S = oracle.default_segments(n)
+    a = ref.step_allpairs_targets(p, targets, S)
+    b = oracle.step_allpairs_targets(p, targets, flavour=oracle.LITERAL)
+    assert a.tobytes() == b.tobytes()
+    assert a.tobytes() != ref.step_allpairs_targets(p, targets, S, chain=0).tobytes()
 
 
 def test_oracle_equals_live_reference_ten_steps(mapc, oracle, ref):
