@@ -21,14 +21,14 @@ struct Plan {
     int block_targets() const { return threads * 2 * pairs; }
 };
 
-// Launch shapes (P, T) with the FMA-pipe efficiency each reaches at large N (tools/ubench,
-// profiles/): all sit on the same 67-72 % plateau, so at large N the choice barely matters, while
+// Launch shapes (P, T) with the fraction of the FP32 peak each reaches at large N (tools/ubench at S = 32,
+// profiles/r02_ubench_probes.txt): all sit on the same 73-78 % plateau, so at large N the choice matters little, while
 // at small N what decides is how evenly the cells fall on the 4 x SMs warp schedulers and how many
 // target lanes the last block leaves idle.  The shape changes neither the arithmetic nor its order
 // (only S does), so it is free to vary with N, the shard size and the device.
 struct Shape { int pairs, threads, minb; float efficiency; };
-constexpr Shape kShapes[6] = {{4, 256, 2, 0.763f}, {4, 128, 4, 0.753f}, {2, 128, 8, 0.754f},
-                              {2, 64, 8, 0.734f},  {1, 64, 16, 0.728f}, {1, 32, 32, 0.722f}};
+constexpr Shape kShapes[6] = {{4, 256, 2, 0.775f}, {4, 128, 4, 0.764f}, {2, 128, 8, 0.749f},
+                              {2, 64, 8, 0.757f},  {1, 64, 16, 0.735f}, {1, 32, 32, 0.730f}};
 
 // S = mapc_plan_segments(n_sources); force_pairs / force_threads != 0 pin the shape (MAPC_PLAN_PAIRS / _THREADS)
 inline Plan make_plan(int n_targets, int S, int sm_count, int force_pairs, int force_threads)
