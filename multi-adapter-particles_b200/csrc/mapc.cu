@@ -392,6 +392,8 @@ struct Switches {
     bool tma;           // MAPC_TMA=1: cp.async.bulk source staging instead of LDG/STS
     bool shfl;          // MAPC_SHFL=1: warp-shuffle broadcast of staged sources instead of LDS broadcast
     bool ring;          // MAPC_RING=0: every target block its own scratch slot (no L2-resident ring)
+    int shape_variant;  // MAPC_SHAPE_VARIANT=v: A/B instantiations of the large-N shapes (csrc/force_shapes.inc)
+    bool chain;         // MAPC_CHAIN=0: consecutive small-N steps wait for the whole previous grid, not per target block
     int wait_timeout_ms;  // MAPC_WAIT_TIMEOUT_MS: bound of every in-kernel wait (peer step flag, ring slot)
     bool mass_in_loop;  // MAPC_MASS_IN_LOOP=1: 12-op pair with the shader's per-pair mass multiply
     bool timers;        // MAPC_TIMERS=0: no "simulate ms" timer at all
@@ -410,6 +412,8 @@ Switches read_switches()
     w.tma = env_int("MAPC_TMA", 0) != 0;
     w.shfl = env_int("MAPC_SHFL", 0) != 0;
     w.ring = env_int("MAPC_RING", 1) != 0;
+    w.chain = env_int("MAPC_CHAIN", 1) != 0;
+    w.shape_variant = env_int("MAPC_SHAPE_VARIANT", 0);
     w.wait_timeout_ms = env_int("MAPC_WAIT_TIMEOUT_MS", 20000);
     w.mass_in_loop = env_int("MAPC_MASS_IN_LOOP", 0) != 0;
     w.timers = env_int("MAPC_TIMERS", 1) != 0;
@@ -486,6 +490,11 @@ struct mapc_compute {
     unsigned long long *stamps = nullptr;      // pinned host: [slot][begin, end] in ns
     unsigned *done = nullptr;                  // device: [0] target blocks integrated this step, [1] cell ticket
     unsigned long long *error_word = nullptr;  // pinned host: [0] != 0 after an in-kernel wait timed out, [1] detail
+    // step-to-step dataflow (StepArgs::block_step): per target block, the id of the last step that integrated it
+    unsigned *block_step = nullptr;
+    unsigned step_counter = 0;                 // id of the last fused unsharded all-pairs step enqueued
+    bool chain_valid = false;                  // block_step describes the newest state, written with chain_key's shape
+    long long chain_key[4] = {0, 0, 0, 0};     // {pairs, threads, n_targets, n_sources} of that step
     unsigned long long *stamp_begin_next = nullptr, *stamp_end_next = nullptr;  // for the next force launch(es)
     unsigned long long fence_write_next = 0;   // != 0: the step's last block writes this value to the fence word
     uint64_t t_next = 0, t_resolved = 0;
@@ -574,9 +583,18 @@ enum Staging { kStageDefault = 0, kStageTma = 1, kStageShfl = 2 };
 
 template <bool FUSE, bool PEER = false, bool INLOOP = false>
 mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::StepArgs &args, cudaStream_t stream,
-                               Staging staging)
+                               Staging staging, int variant = 0)
 {
     if (args.segs.count == 0 || args.i_cnt <= 0) return MAPC_OK;
+    if (FUSE && !PEER && !INLOOP && staging == kStageDefault && variant != 0) {
+#define MAPC_SHAPE(P, T, TJ, U, MINB, ORDER, HAS_TMA)
+#define MAPC_SHAPE_VARIANT(V, P, T, TJ, U, MINB, ORDER)                                         \
+        if (variant == V && pl.pairs == P && pl.threads == T)                                   \
+            return launch_force<P, T, TJ, U, MINB, ORDER, FUSE && !PEER && !INLOOP, false, false, false>(c, args, stream);
+#include "force_shapes.inc"
+#undef MAPC_SHAPE_VARIANT
+#undef MAPC_SHAPE
+    }
     constexpr bool kAlt = FUSE && !PEER && !INLOOP;   // the alternatives are instantiated for this path only
     const bool tma = kAlt && staging == kStageTma;
     const bool shfl = kAlt && staging == kStageShfl;
@@ -679,6 +697,8 @@ mapc_status create_common(mapc_compute **out, uint32_t n, int device, int rank, 
         memset(c->stamps, 0, 2 * mapc_compute::kTimerSlots * sizeof(unsigned long long));
         MAPC_CUDA(cudaMalloc(&c->done, 64));
         MAPC_CUDA(cudaMemset(c->done, 0, 64));
+        MAPC_CUDA(cudaMalloc(&c->block_step, ((size_t)c->n_local / 64 + 2) * sizeof(unsigned)));
+        MAPC_CUDA(cudaMemset(c->block_step, 0, ((size_t)c->n_local / 64 + 2) * sizeof(unsigned)));
         MAPC_CUDA(cudaHostAlloc((void **)&c->error_word, 2 * sizeof(unsigned long long),
                                 cudaHostAllocPortable | cudaHostAllocMapped));
         c->error_word[0] = c->error_word[1] = 0;
@@ -892,6 +912,7 @@ mapc_status mapc_compute_destroy(mapc_compute *c)
     if (c->slot_gen) cudaFree(c->slot_gen);
     if (c->counters) cudaFree(c->counters);
     if (c->done) cudaFree(c->done);
+    if (c->block_step) cudaFree(c->block_step);
     if (c->stamps) cudaFreeHost(c->stamps);
     if (c->error_word) cudaFreeHost(c->error_word);
     if (c->ev_integrated) cudaEventDestroy(c->ev_integrated);
@@ -953,6 +974,7 @@ mapc_status mapc_compute_upload(mapc_compute *c, const mapc_posvelo *host, uint3
     c->gather_pending[0] = c->gather_pending[1] = false;
     MAPC_TRY(mapc_compute_wait_for_gpu(c));  // InitializeParticles ends with WaitForGpu, Compute.cpp:922
     c->has_state = true;
+    c->chain_valid = false;
     return MAPC_OK;
 }
 
@@ -1045,6 +1067,8 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
 {
     const uint32_t r = 1u - b;  // read side (reads 1-b, writes b)
     bool use_peer = false;
+    const bool chain_was_valid = c->chain_valid;
+    c->chain_valid = false;     // set again below by a step that publishes block_step for exactly this state
 
     if (c->peer_mode && mode == MAPC_FORCE_WELL)
         // a well step would overwrite this rank's packed positions without waiting for the peers that may
@@ -1090,6 +1114,20 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             args.done = c->done;
             args.error_word = c->error_word;
             args.wait_timeout_ns = (unsigned long long)sw.wait_timeout_ms * 1000000ull;
+            // Step-to-step dataflow: an unsharded fused step publishes, per target block, that the block is
+            // integrated; the NEXT such step with the same shape and counts, launched with programmatic
+            // dependent launch and default staging, then waits per cell for the blocks it reads instead of for
+            // the whole previous grid -- its cells run in the drain of the previous step (small N: the drain and
+            // ramp of a ~50 us grid are a quarter of the step).  Not with the scratch ring (large N: cells of
+            // milliseconds, nothing to gain).
+            const long long chain_key[4] = {pl.pairs, pl.threads, n_targets, n_sources};
+            const bool publishes = c->world == 1 && fuse;
+            if (publishes) {
+                args.block_step = c->block_step;
+                args.step_id = ++c->step_counter;
+                args.wait_prev = (sw.chain && c->pdl_next && chain_was_valid && !sc.ring && !sw.tma && !sw.shfl &&
+                                  memcmp(chain_key, c->chain_key, sizeof(chain_key)) == 0) ? 1 : 0;
+            }
             args.stamp_begin = c->stamp_begin_next;   // consumed by the first launch of the step
             args.stamp_end = c->stamp_end_next;       // every launch: whichever finishes the step writes it
             args.fence_word = c->fence_write_next ? (unsigned long long *)c->fence->word : nullptr;
@@ -1118,7 +1156,7 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             const Staging staging = sw.shfl ? kStageShfl : (sw.tma ? kStageTma : kStageDefault);
             auto launch = [&](cudaStream_t st) -> mapc_status {
                 if (inloop) return launch_force_shape<true, false, true>(c, pl, args, st, staging);
-                return fuse ? launch_force_shape<true>(c, pl, args, st, staging)
+                return fuse ? launch_force_shape<true>(c, pl, args, st, staging, sw.shape_variant)
                             : launch_force_shape<false>(c, pl, args, st, staging);
             };
             if (single_grid) {
@@ -1165,6 +1203,10 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
                 MAPC_CUDA(cudaEventRecord(c->ev_remote_done, c->compute2));
                 MAPC_CUDA(cudaStreamWaitEvent(c->compute, c->ev_remote_done, 0));
             }
+            }
+            if (publishes && !sc.ring) {
+                c->chain_valid = true;
+                memcpy(c->chain_key, chain_key, sizeof(chain_key));
             }
             if (!fuse) {
                 mapc::integrate_kernel<<<(n_targets + 255) / 256, 256, 0, c->compute>>>(
@@ -1442,6 +1484,7 @@ mapc_status mapc_compute_copy_state(mapc_compute *dst, mapc_compute *src)
     dst->mode = src->mode;
     dst->gather_pending[0] = dst->gather_pending[1] = false;
     dst->has_state = true;
+    dst->chain_valid = false;
     return mapc_compute_wait_for_gpu(dst);  // Compute.cpp:409
 }
 
@@ -1842,6 +1885,7 @@ mapc_status mapc_compute_init_particles(mapc_compute *c, uint32_t seed)
     c->gather_pending[0] = c->gather_pending[1] = false;
     MAPC_TRY(mapc_compute_wait_for_gpu(c));  // InitializeParticles ends with WaitForGpu, Compute.cpp:922
     c->has_state = true;
+    c->chain_valid = false;
     return MAPC_OK;
 }
 

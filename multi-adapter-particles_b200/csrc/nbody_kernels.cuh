@@ -205,6 +205,15 @@ struct StepArgs {
     // WaitForGpu reports the step as failed instead of the GPU hanging.
     unsigned long long wait_timeout_ns;
     unsigned long long *error_word;
+    // Step-to-step dataflow (batched small-N steps): block_step[ib] = id of the last step
+    // whose target block ib has been integrated (published by every fused step when not null).  A launch with
+    // wait_prev != 0 does NOT wait for the whole previous grid (griddepcontrol.wait): each cell waits only for
+    // the target blocks of step step_id - 1 it reads -- its own targets and the bodies of its source segment --
+    // so its math overlaps the drain of the previous step.  Requires the previous step to have had the same
+    // launch shape and body counts (the host decides).
+    unsigned *block_step;
+    unsigned step_id;
+    int wait_prev;
     // fence signal from inside the kernel (ID3D12CommandQueue::Signal after the Dispatch, Compute.cpp:999):
     // the same last block stores fence_value to the fence word (pinned host memory) -- or null
     unsigned long long *fence_word;
@@ -328,7 +337,7 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
     // one drains, and do not touch the previous step's output before that grid has completely finished.
     // Both are no-ops for a launch without the programmatic-serialization attribute.
     pdl_launch_dependents();
-    pdl_wait();
+    if (!a.wait_prev) pdl_wait();
     unsigned cell = blockIdx.x;
     if (a.ticket != nullptr) {
         if (tid == 0) s_cell = atomicAdd(a.ticket, 1u);
@@ -361,6 +370,30 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
         const int seg = a.segs.ids[kseg];
         int j0, j1;
         segment_range(a.n_sources, a.S, seg, j0, j1);
+        if (a.wait_prev) {
+            // dataflow instead of a grid-wide wait: the previous step must have integrated this cell's own
+            // target block and the target blocks that hold the bodies of its source segment
+            if (tid == 0) {
+                const unsigned want = a.step_id - 1u;
+                const unsigned long long t0 = global_timer_ns();
+                int first = j1 > j0 ? j0 / kBlockTargets : ib, last = j1 > j0 ? (j1 - 1) / kBlockTargets : ib;
+                if (last >= a.n_iblocks) last = a.n_iblocks - 1;   // sources past the dispatched targets are never rewritten
+                for (int tb = first - 1; tb <= last; ++tb) {
+                    const int blk = tb < first ? ib : tb;          // first pass: the own target block
+                    if (blk >= a.n_iblocks) continue;
+                    while ((int)(load_acquire_gpu(a.block_step + blk) - want) < 0) {
+                        __nanosleep(64);
+                        if (a.error_word != nullptr && global_timer_ns() - t0 > a.wait_timeout_ns) {
+                            a.error_word[1] = (unsigned long long)blk;
+                            a.error_word[0] = 3ull;     // a target block of the previous step never completed
+                            __threadfence_system();
+                            break;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
 
         // targets: thread owns local bodies i_block + q*T + tid, q = 0..2P-1 (coalesced in q);
         // pair p = (q = 2p, q = 2p+1).  Out-of-range lanes are clamped and never stored.
@@ -372,8 +405,8 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
             int ib2 = i_block + (2 * p + 1) * T + tid;
             ia = ia < a.i_cnt ? ia : a.i_cnt - 1;
             ib2 = ib2 < a.i_cnt ? ib2 : a.i_cnt - 1;
-            const float4 ta = pos[a.i_first + ia];
-            const float4 tb = pos[a.i_first + ib2];
+            const float4 ta = __ldcg(pos + a.i_first + ia);    // L2: may have been written by a grid still running
+            const float4 tb = __ldcg(pos + a.i_first + ib2);
             nxi[p] = make_float2(-ta.x, -tb.x);
             nyi[p] = make_float2(-ta.y, -tb.y);
             nzi[p] = make_float2(-ta.z, -tb.z);
@@ -394,7 +427,7 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
 #pragma unroll
                 for (int l = 0; l < kLoads; ++l) {
                     const int j = j0 + l * T + tid;
-                    stage[l] = j < j1 ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    stage[l] = j < j1 ? __ldcg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int l = 0; l < kLoads; ++l) tile[0][l * T + tid] = stage[l];
@@ -419,7 +452,7 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
 #pragma unroll
                 for (int l = 0; l < kLoads; ++l) {
                     const int j = jt + TJ + l * T + tid;
-                    stage[l] = j < j1 ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    stage[l] = j < j1 ? __ldcg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             const int cnt = (j1 - jt) < TJ ? (j1 - jt) : TJ;
@@ -565,7 +598,7 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                         }
                         const float4 *srcpv = reinterpret_cast<const float4 *>(a.in + i);
                         float4 pos_out, vel_out;
-                        integrate_body(srcpv[0], srcpv[1], sx, sy, sz, a.dt, a.damping, pos_out, vel_out);
+                        integrate_body(__ldcg(srcpv), __ldcg(srcpv + 1), sx, sy, sz, a.dt, a.damping, pos_out, vel_out);
                         float4 *dst = reinterpret_cast<float4 *>(a.out + i);
                         dst[0] = pos_out;
                         dst[1] = vel_out;
@@ -596,6 +629,9 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                             __threadfence_system();
                         }
                     }
+                    // last: this target block of this step is in place (after the step's counters were re-armed,
+                    // so a dependent cell of the NEXT step can never touch them early)
+                    if (a.block_step != nullptr) store_release_gpu(a.block_step + ib, a.step_id);
                 }
             }
         }

@@ -221,6 +221,61 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
     return 0;
 }
 
+// `steps` consecutive fused steps of an unsharded handle with the step-to-step dataflow flags of csrc/mapc.cu: the
+// first step waits for "the previous grid" (nothing to wait for here) and publishes block_step, every later one is
+// launched with wait_prev = 1 and waits per cell for the target blocks it reads.  Blocks run one after the other in
+// the emulation, so a wait can only spin forever if it names a block that is never published or a wrong step id
+// -- which is what this checks (with `poison`, flags of the blocks a step must NOT need are left behind).
+// state: n PosVelo in, the state after `steps` steps out.  Returns 0, -1 unknown shape, -3 a wait would not end.
+int emu_steps_chained(mapc_posvelo *state, int n, int steps, float dt, float damping, int S, int pairs, int threads,
+                      int block_order)
+{
+    const int per_block = threads * 2 * pairs;
+    const int n_iblocks = (n + per_block - 1) / per_block;
+    std::vector<PV> side[2] = {std::vector<PV>(n), std::vector<PV>(n)};
+    std::memcpy(side[0].data(), state, (size_t)n * sizeof(PV));
+    std::memcpy(side[1].data(), state, (size_t)n * sizeof(PV));
+    std::vector<float4> packed[2] = {std::vector<float4>(n), std::vector<float4>(n)};
+    for (int sd = 0; sd < 2; ++sd)
+        for (int i = 0; i < n; ++i) packed[sd][i] = make_float4(state[i].pos[0], state[i].pos[1], state[i].pos[2], state[i].pos[3]);
+    std::vector<float4> partial((size_t)n_iblocks * S * per_block);
+    std::vector<unsigned> counters(n / 64 + 2, 0u), block_step(n / 64 + 2, 0u);
+    unsigned done[2] = {0, 0};
+    unsigned long long error_word[2] = {0, 0};
+    int b = 0;   // write side; both sides start alike, the first step reads side 1
+    for (int k = 0; k < steps; ++k, b ^= 1) {
+        StepArgs a{};
+        a.pos = packed[1 - b].data();
+        a.partial = partial.data();
+        a.scratch_blocks = n_iblocks;
+        a.i_first = 0;
+        a.i_cnt = n;
+        a.n_sources = n;
+        a.S = S;
+        a.n_iblocks = n_iblocks;
+        a.counters = counters.data();
+        a.in = reinterpret_cast<const mapc_posvelo *>(side[1 - b].data());
+        a.out = reinterpret_cast<mapc_posvelo *>(side[b].data());
+        a.pos_next = packed[b].data();
+        a.dt = dt;
+        a.damping = damping;
+        a.done = done;
+        a.block_step = block_step.data();
+        a.step_id = (unsigned)(k + 1);
+        a.wait_prev = k > 0 ? 1 : 0;
+        a.error_word = error_word;
+        a.wait_timeout_ns = 2000000000ull;   // a wait that cannot end is reported after 2 s instead of hanging the test
+        a.segs.count = S;
+        for (int s = 0; s < S; ++s) a.segs.ids[s] = s;
+        if (!launch_force(pairs, threads, true, false, false, MAPC_CHAIN_SOURCES, 0, a, block_order)) return -1;
+        if (error_word[0] != 0) return -3;
+        for (int ib = 0; ib < n_iblocks; ++ib)
+            if (block_step[ib] != (unsigned)(k + 1)) return -3;
+    }
+    std::memcpy(state, side[1 - b].data(), (size_t)n * sizeof(PV));
+    return 0;
+}
+
 // The literal CSMain step (well_step_kernel) of one rank's shard [i_first, i_first + n_local): out and
 // pos_next_out as above.  Also runs pack_positions_kernel over `in` into packed_out (n float4).
 int emu_step_well(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next_out, float *packed_out, int n,

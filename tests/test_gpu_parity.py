@@ -499,6 +499,62 @@ def test_batched_steps_equal_single_steps(mapc, gpu):
         assert c.GetSharedHandles().m_bufferIndex == 1      # 7 steps: odd number of flips
 
 
+def test_chained_steps_are_bit_identical_to_grid_wide_waits(mapc, gpu):
+    """Consecutive small-N steps are chained by per-target-block flags (a cell waits only for the blocks of the
+    previous step it reads) instead of waiting for the whole previous grid.  Same cells, same
+    arithmetic: 120 steps issued in batches, as single calls, with MAPC_CHAIN=0 and with every launch shape forced
+    must end in the same bytes -- and a stale flag (wrong block / wrong step) would show as garbage or a timeout."""
+    for n, seed in ((10_000, 1), (3_000, 2), (777, 3)):
+        p = mapc.ic.uniform_sphere(n, 2000.0 * (n / 10_000.0) ** (1 / 3), seed, speed=1.0)
+
+        def run(batch, steps=120):
+            with mapc.Compute(n, 0) as c:
+                c.Upload(p)
+                if batch > 1:
+                    for k in range(0, steps, batch):
+                        c.SimulateSteps(n, min(batch, steps - k))
+                else:
+                    for _ in range(steps):
+                        c.Simulate(n, 0)
+                c.WaitForGpu()
+                return c.Download()
+
+        try:
+            os.environ["MAPC_CHAIN"] = "0"
+            ref = run(40)
+        finally:
+            os.environ.pop("MAPC_CHAIN", None)
+        assert run(40).tobytes() == ref.tobytes(), (n, "batches of 40")
+        assert run(1).tobytes() == ref.tobytes(), (n, "single calls")
+        assert run(7).tobytes() == ref.tobytes(), (n, "batches of 7")
+        try:
+            for pairs, threads in ((1, 32), (1, 64), (2, 64), (2, 128), (4, 128)):
+                os.environ["MAPC_PLAN_PAIRS"], os.environ["MAPC_PLAN_THREADS"] = str(pairs), str(threads)
+                assert run(30, 60).tobytes() == run(1, 60).tobytes(), (n, pairs, threads)
+        finally:
+            os.environ.pop("MAPC_PLAN_PAIRS", None)
+            os.environ.pop("MAPC_PLAN_THREADS", None)
+    # a change of n_active between steps breaks the chain (other blocks, other sources): still correct
+    n = 4096
+    p = gentle_sphere(mapc, n, seed=12, speed=1.0)
+    with mapc.Compute(n, 0) as c:
+        c.Upload(p)
+        for k in range(12):
+            c.Simulate(n if k % 3 else n // 2, 0)
+        c.WaitForGpu()
+        mixed = c.Download()
+    try:
+        os.environ["MAPC_PDL"] = "0"
+        with mapc.Compute(n, 0) as c:
+            c.Upload(p)
+            for k in range(12):
+                c.Simulate(n if k % 3 else n // 2, 0)
+                c.WaitForGpu()
+            assert c.Download().tobytes() == mixed.tobytes()
+    finally:
+        os.environ.pop("MAPC_PDL", None)
+
+
 @pytest.mark.parametrize("n", [1, 2, 63, 65, 129])
 def test_tiny_and_ragged_sizes(mapc, oracle, gpu, n):
     """Edge sizes: a single body (self-pair only: exactly zero force), sizes straddling the 64-body tile."""

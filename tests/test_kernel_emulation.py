@@ -37,6 +37,8 @@ def emu():
     lib.emu_local_targets.argtypes = [ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ci]
     lib.emu_step_well.restype = ci
     lib.emu_step_well.argtypes = [vp, vp, vp, vp, ci, ci, cf, cf, ci, ci]
+    lib.emu_steps_chained.restype = ci
+    lib.emu_steps_chained.argtypes = [vp, ci, ci, cf, cf, ci, ci, ci, ci]
     lib.emu_init_particles.restype = ci
     lib.emu_init_particles.argtypes = [vp, vp, vp, vp, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]
     return lib
@@ -182,6 +184,23 @@ def test_well_and_pack_kernels(emu, oracle, mapc, n, n_active, shard):
     assert got[:first].tobytes() == stale[:first].tobytes()                        # another rank's shard
     assert mirror[lo:hi].tobytes() == ref["pos"][lo:hi].tobytes()
     assert packed.tobytes() == p["pos"].tobytes()
+
+
+@pytest.mark.parametrize("shape,n", [((1, 32), 300), ((1, 64), 1000), ((2, 64), 1100), ((4, 128), 2500)])
+def test_chained_steps_equal_oracle_trajectory_bitwise(emu, oracle, mapc, shape, n):
+    """Step-to-step dataflow (StepArgs::block_step / wait_prev: a cell waits for the target blocks of the previous
+    step it reads instead of for the whole previous grid): four ping-pong steps whose launches 2..4 carry
+    wait_prev, against the oracle's trajectory.  The emulation runs blocks one at a time, so what it pins is that
+    every wait names blocks that exist and are published with the right step id (a wrong one is reported as a
+    timeout), that the flags are published for every block, and that the L2 loads read the right side."""
+    p = mapc.ic.uniform_sphere(n, 300.0, seed=n, speed=1.0)
+    S = mapc.plan_segments(n)
+    state = np.ascontiguousarray(p.copy())
+    assert emu.emu_steps_chained(state.ctypes.data, n, 4, 0.1, 1.0, S, shape[0], shape[1], 0) == 0
+    ref = p
+    for _ in range(4):
+        ref = oracle.step_allpairs(ref, S=S, flavour=oracle.MIRRORED)
+    assert state.tobytes() == ref.tobytes()
 
 
 @pytest.mark.parametrize("n,first,count", [(1000, 0, 1000), (1001, 0, 1001), (4096, 1024, 1024)])
