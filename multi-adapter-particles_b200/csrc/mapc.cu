@@ -486,6 +486,9 @@ struct mapc_compute {
     bool t_pending[kTimerSlots] = {};
     int t_steps[kTimerSlots] = {};   // steps covered by the slot's event pair (batched Simulate)
     bool t_stamped[kTimerSlots] = {};          // slot timed by in-kernel %globaltimer stamps, not events
+    bool t_begin_is_prev_end[kTimerSlots] = {};  // chained step: its time runs from the previous step's end stamp
+    int t_cur_slot = 0;                        // slot of the enqueue in progress
+    unsigned long long last_end_ns = 0;        // end stamp of the newest resolved stamped slot
     uint64_t t_fence_value[kTimerSlots] = {};  // fence value signalled after the slot's step(s)
     unsigned long long *stamps = nullptr;      // pinned host: [slot][begin, end] in ns
     unsigned *done = nullptr;                  // device: [0] target blocks integrated this step, [1] cell ticket
@@ -521,7 +524,12 @@ void resolve_timers(mapc_compute *c, bool block)
                     if (!block) return;
                     if (mapc_fence_wait_host(c->fence, c->t_fence_value[slot], 60000) != MAPC_OK) return;
                 }
-                const unsigned long long t0 = c->stamps[2 * slot], t1 = c->stamps[2 * slot + 1];
+                // A chained step starts inside the drain of the previous one (its cells wait per target block, not
+                // for the grid), so "first cell start -> last integrate" would count the overlap twice: its time
+                // runs from the previous step's end stamp instead, like back-to-back dispatches on one queue.
+                const unsigned long long t0 = c->t_begin_is_prev_end[slot] ? c->last_end_ns : c->stamps[2 * slot];
+                const unsigned long long t1 = c->stamps[2 * slot + 1];
+                c->last_end_ns = t1;
                 have = t1 > t0 && t0 != 0;
                 ms = have ? (float)((double)(t1 - t0) * 1e-6) : 0.f;
             } else {
@@ -991,6 +999,7 @@ mapc_status mapc_compute_download(mapc_compute *c, mapc_posvelo *host, uint32_t 
     MAPC_CUDA(cudaMemcpyAsync(host, c->posvelo[side] + (first - c->i_first),
                               (size_t)count * sizeof(mapc_posvelo), cudaMemcpyDeviceToHost, c->compute));
     MAPC_CUDA(cudaStreamSynchronize(c->compute));
+    c->chain_valid = false;
     return MAPC_OK;
 }
 
@@ -1030,6 +1039,8 @@ static mapc_status enqueue_steps(mapc_compute *c, uint32_t b0, int n_targets, in
     // N = 10,000), so the fused all-pairs kernel stamps %globaltimer itself; the event pair remains for
     // the well kernel and the unfused path.
     const bool stamped = timers && mode == MAPC_FORCE_ALLPAIRS && n_targets > 0 && sw.fuse && !sw.timer_events;
+    c->t_cur_slot = slot;
+    c->t_begin_is_prev_end[slot] = false;
     if (stamped) {
         c->stamps[2 * slot] = 0;
         c->stamps[2 * slot + 1] = 0;
@@ -1129,6 +1140,10 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
                                   memcmp(chain_key, c->chain_key, sizeof(chain_key)) == 0) ? 1 : 0;
             }
             args.stamp_begin = c->stamp_begin_next;   // consumed by the first launch of the step
+            if (args.wait_prev && args.stamp_begin != nullptr) {   // a chained step's time runs from the previous end stamp
+                args.stamp_begin = nullptr;
+                c->t_begin_is_prev_end[c->t_cur_slot] = true;
+            }
             args.stamp_end = c->stamp_end_next;       // every launch: whichever finishes the step writes it
             args.fence_word = c->fence_write_next ? (unsigned long long *)c->fence->word : nullptr;
             args.fence_value = c->fence_write_next;
@@ -1324,6 +1339,7 @@ mapc_status mapc_compute_wait_for_gpu(mapc_compute *c)
         return fail(MAPC_ERR_CUDA, "fence at %llu after drain, expected >= %llu",
                     (unsigned long long)mapc_fence_completed_value(c->fence), (unsigned long long)v);
     resolve_timers(c, true);
+    c->chain_valid = false;   // the device is idle: the next step has nothing to chain to (and its timer starts afresh)
     return MAPC_OK;
 }
 
