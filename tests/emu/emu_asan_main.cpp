@@ -13,6 +13,10 @@ extern "C" int emu_step_allpairs(const void *in, void *out, float *pos_next_out,
                       float dt, float damping, int S, int pairs, int threads, int fuse, int mass_in_loop,
                       int world, int peer, int block_order, int chain, int staging, int ring_slots,
                       unsigned long long *info);
+extern "C" int emu_steps_chained(void *state, int n, int steps, float dt, float damping, int S, int pairs, int threads,
+                                 int block_order);
+extern "C" int emu_init_particles(void *side_a, void *side_b, float *packed_a, float *packed_b, unsigned n,
+                                  unsigned i_first, unsigned n_local, unsigned seed);
 extern "C" int emu_step_well(const void *in, void *out, float *pos_next_out, float *packed_out, int n,
                   int n_active, float dt, float damping, int i_first, int n_local);
 int main() {
@@ -37,6 +41,20 @@ int main() {
                     ++runs;
                 }
         emu_step_well(in.data(), out.data(), mirror.data(), packed.data(), n, n, 0.1f, 1.f, 0, n);
+        // chained steps (per-target-block flags) and the initial-conditions kernel, exactly-sized buffers
+        for (auto &sh : shapes) {
+            if (n > 1100 && sh[0] * sh[1] < 128) continue;
+            std::vector<PV> state = in;
+            int rc = emu_steps_chained(state.data(), n, 3, 0.1f, 1.f, 32, sh[0], sh[1], 0);
+            if (rc != 0) { printf("chained rc %d n %d shape %d %d\n", rc, n, sh[0], sh[1]); return 1; }
+            ++runs;
+        }
+        {
+            const unsigned first = n >= 4 ? n / 4 : 0, count = n >= 4 ? n / 2 : n;
+            std::vector<PV> a(count), b(count); std::vector<float> pa(4*n), pb(4*n);
+            emu_init_particles(a.data(), b.data(), pa.data(), pb.data(), n, first, count, 99u);
+            ++runs;
+        }
     }
     printf("asan emulation runs: %d ok\n", runs);
     return 0;
