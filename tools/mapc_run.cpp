@@ -18,6 +18,8 @@
 //   --load file / --dump file   raw little-endian PosVelo[N] (32 bytes per body) in / out
 //   --device d --render-device d   CUDA devices of producer and consumer (may differ: peer copy)
 //   --no-consumer      skip the consumer (pure simulation loop)
+//   --async            the reference's async mode: consumer on the producer's device, no copies
+//                      (Particles.cpp:202-207 chooses it when render and compute adapter are the same)
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -42,6 +44,7 @@ struct Options {
     std::uint32_t seed = 1;
     int device = 0, render_device = -1;
     bool consumer = true;
+    bool async_mode = false;
 };
 
 [[noreturn]] void usage(const char *msg)
@@ -75,6 +78,7 @@ Options parse(int argc, char **argv)
         else if (a == "--device") o.device = std::atoi(val());
         else if (a == "--render-device") o.render_device = std::atoi(val());
         else if (a == "--no-consumer") o.consumer = false;
+        else if (a == "--async") o.async_mode = true;
         else usage(("unknown option " + a).c_str());
     }
     if (o.num_sim < 0) o.num_sim = (int)o.n;
@@ -145,7 +149,7 @@ int main(int argc, char **argv)
         }
 
         std::unique_ptr<mapc::HeadlessRender> render;
-        if (o.consumer) render = std::make_unique<mapc::HeadlessRender>(compute, o.render_device);
+        if (o.consumer) render = std::make_unique<mapc::HeadlessRender>(compute, o.render_device, o.async_mode);
 
         const auto t0 = std::chrono::steady_clock::now();
         for (int k = 0; k < o.steps; ++k) {
