@@ -9,6 +9,8 @@
 #   <tag>_bench_reference.json      bench.py --impl reference
 #   <tag>_bench_n10000*.json        config 2, single calls and batches of 50
 #   <tag>_bench_well.json           bench.py --mode well (the reference's shipped kernel, HBM roofline)
+#   <tag>_soak.txt                  tools/soak.py: 20,000 chained steps / 100 ring steps, bitwise against the protocols off
+#   <tag>_compute_sanitizer.txt     tools/gpu_sanitizer.sh (memcheck / racecheck / synccheck), when SANITIZER=1
 #   <tag>_launches.csv              ncu launch list of the bench command (gpu__time_duration.sum per launch)
 #   <tag>_force_full.ncu-rep/.csv   ncu --set full of one force kernel launch at N = 262,144 + its raw page as CSV
 #   <tag>_force_noring_dram.csv     dram bytes of the same launch with MAPC_RING=0 (one scratch slot per target block)
@@ -41,6 +43,8 @@ timeout 300 python bench.py --bodies 10000 --steps 1000 --warmup 50 --no-l2-flus
     > "$OUT/${TAG}_bench_n10000.json" 2>> "$ERR"
 timeout 300 python bench.py --bodies 10000 --steps 1000 --warmup 50 --batch 50 --no-cpu-baseline --headline-only \
     > "$OUT/${TAG}_bench_n10000_batched.json" 2>> "$ERR"
+step "soak: chained steps and scratch ring, bit-identity over many steps"
+timeout 600 python tools/soak.py > "$OUT/${TAG}_soak.txt" 2>> "$ERR"; cat "$OUT/${TAG}_soak.txt" >&2
 step "bench, well mode"
 timeout 300 python bench.py --mode well --steps 20 --warmup 5 > "$OUT/${TAG}_bench_well.json" 2>> "$ERR"
 tail -c 400 "$OUT/${TAG}_bench_well.json" >&2
@@ -66,6 +70,11 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:well
 [ -f "$OUT/${TAG}_well_full.ncu-rep" ] && ncu -i "$OUT/${TAG}_well_full.ncu-rep" --page raw --csv > "$OUT/${TAG}_well_full.csv" 2>/dev/null
 python tools/ncu_traffic.py "$OUT" "$TAG" > "$OUT/${TAG}_ncu_traffic.json" 2>> "$ERR"
 cat "$OUT/${TAG}_ncu_traffic.json" >&2
+fi
+if [ "${SANITIZER:-0}" = 1 ]; then
+step "compute-sanitizer"
+bash tools/gpu_sanitizer.sh "$TAG" 2>/dev/null
+tail -n 40 "$OUT/${TAG}_compute_sanitizer.txt" >&2
 fi
 step "done"
 tail -5 "$ERR" >&2
