@@ -27,8 +27,9 @@ struct Plan {
 // target lanes the last block leaves idle.  The shape changes neither the arithmetic nor its order
 // (only S does), so it is free to vary with N, the shard size and the device.
 struct Shape { int pairs, threads, minb; float efficiency; };
-constexpr Shape kShapes[6] = {{4, 256, 2, 0.775f}, {4, 128, 4, 0.764f}, {2, 128, 8, 0.749f},
-                              {2, 64, 8, 0.757f},  {1, 64, 16, 0.735f}, {1, 32, 32, 0.730f}};
+constexpr Shape kShapes[7] = {{4, 256, 2, 0.775f}, {4, 128, 4, 0.764f}, {2, 128, 8, 0.749f},
+                              {2, 64, 8, 0.757f},  {1, 64, 16, 0.735f}, {1, 32, 32, 0.730f},
+                              {1, 128, 8, 0.0f}};   // (1,128): only when forced (A/B for small N)
 
 // S = mapc_plan_segments(n_sources); force_pairs / force_threads != 0 pin the shape (MAPC_PLAN_PAIRS / _THREADS)
 inline Plan make_plan(int n_targets, int S, int sm_count, int force_pairs, int force_threads)
