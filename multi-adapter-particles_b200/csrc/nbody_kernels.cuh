@@ -589,12 +589,23 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                     const int row = q * T + tid;
                     const int i = i_block + row;
                     if (i < a.i_cnt) {
+                        // canonical left-to-right fold of the S partials; the loads of a batch are issued together
+                        // (they are L2 round trips: one at a time they would be the longest serial piece of a
+                        // small-N step), the additions stay in segment order
                         float sx = 0.f, sy = 0.f, sz = 0.f;
-                        for (int s = 0; s < a.S; ++s) {
-                            const float4 pp = __ldcg(part + (size_t)s * kBlockTargets + row);
-                            sx = __fadd_rn(sx, pp.x);
-                            sy = __fadd_rn(sy, pp.y);
-                            sz = __fadd_rn(sz, pp.z);
+                        constexpr int kBatch = 8;
+                        for (int s0 = 0; s0 < a.S; s0 += kBatch) {
+                            float4 pp[kBatch];
+#pragma unroll
+                            for (int k = 0; k < kBatch; ++k)
+                                if (s0 + k < a.S) pp[k] = __ldcg(part + (size_t)(s0 + k) * kBlockTargets + row);
+#pragma unroll
+                            for (int k = 0; k < kBatch; ++k)
+                                if (s0 + k < a.S) {
+                                    sx = __fadd_rn(sx, pp[k].x);
+                                    sy = __fadd_rn(sy, pp[k].y);
+                                    sz = __fadd_rn(sz, pp[k].z);
+                                }
                         }
                         const float4 *srcpv = reinterpret_cast<const float4 *>(a.in + i);
                         float4 pos_out, vel_out;
