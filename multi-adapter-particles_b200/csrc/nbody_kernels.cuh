@@ -198,7 +198,9 @@ struct StepArgs {
     // block that integrates the LAST target block of the step stamps it when it is done
     unsigned long long *stamp_begin;   // pinned host memory, or null
     unsigned long long *stamp_end;     // pinned host memory, or null
-    unsigned *done;                    // target blocks integrated so far this step (device); never null for FUSE
+    unsigned *done;                    // device, never null for FUSE: [0] target blocks integrated so far this step,
+                                       // [1] the cell ticket, [2] id of the last step whose host-visible completion
+                                       // (stamp, fence word) has been written
     // Every in-kernel wait (a peer's step flag, a scratch-ring slot) is bounded: after wait_timeout_ns the
     // waiting block stores MAPC_ERR_TIMEOUT-style evidence to error_word (pinned host memory: [0] = 1 peer
     // flag / 2 ring slot, [1] = what it waited for) and carries on, so the grid always terminates and
@@ -623,7 +625,8 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                 if (tid == 0) {
                     a.counters[ib] = 0u;  // ready for the next step
                     if (a.slot_gen != nullptr) store_release_gpu(a.slot_gen + slot, (unsigned)(ib / a.scratch_blocks) + 1u);
-                    if (atomicAdd(a.done, 1u) + 1u == (unsigned)a.n_iblocks) {
+                    const bool step_done = atomicAdd(a.done, 1u) + 1u == (unsigned)a.n_iblocks;
+                    if (step_done) {
                         // the step is complete: this was its last target block.  Re-arm the step's counters.
                         __threadfence();
                         *a.done = 0u;
@@ -631,18 +634,31 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
                         if (a.slot_gen != nullptr)
                             for (int s = 0; s < a.scratch_blocks; ++s) a.slot_gen[s] = 0u;
                         __threadfence();
+                    }
+                    // this target block of this step is in place: published after the step's counters were
+                    // re-armed (a dependent cell of the NEXT step can never touch them early) and before the
+                    // system-scope stores below (they cross PCIe; the next step need not wait for them)
+                    if (a.block_step != nullptr) store_release_gpu(a.block_step + ib, a.step_id);
+                    if (step_done) {
+                        // Host-visible completion (timer stamp, fence value).  Chained steps finish in order,
+                        // but their last blocks are different threads: the fence word must never be seen going
+                        // backwards, so a chained step writes it only after the previous step has (done[2]).
+                        if (a.block_step != nullptr && a.wait_prev) {
+                            const unsigned long long t0 = global_timer_ns();
+                            while ((int)(load_acquire_gpu(a.done + 2) - (a.step_id - 1u)) < 0) {
+                                __nanosleep(32);
+                                if (a.error_word != nullptr && global_timer_ns() - t0 > a.wait_timeout_ns) break;
+                            }
+                        }
                         if (a.stamp_end != nullptr) {
                             *a.stamp_end = global_timer_ns();
-                            __threadfence_system();
+                            __threadfence_system();      // the stamp is visible before the fence value that announces it
                         }
-                        if (a.fence_word != nullptr) {
+                        if (a.fence_word != nullptr)
                             *reinterpret_cast<volatile unsigned long long *>(a.fence_word) = a.fence_value;
-                            __threadfence_system();
-                        }
+                        __threadfence_system();
+                        if (a.block_step != nullptr) store_release_gpu(a.done + 2, a.step_id);
                     }
-                    // last: this target block of this step is in place (after the step's counters were re-armed,
-                    // so a dependent cell of the NEXT step can never touch them early)
-                    if (a.block_step != nullptr) store_release_gpu(a.block_step + ib, a.step_id);
                 }
             }
         }

@@ -128,7 +128,7 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
         std::vector<float4> pos_next(n, make_float4(nan, nan, nan, nan));
         std::vector<unsigned> counters(n_local / 64 + 2, 0u);
         std::vector<unsigned> slot_gen(slots, 0u);
-        unsigned done[2] = {0, 0};   // [0] target blocks integrated, [1] cell ticket
+        unsigned done[3] = {0, 0, 0};   // [0] target blocks integrated, [1] cell ticket, [2] last step completed host-visibly
         unsigned long long stamps[2] = {0, 0};
 
         StepArgs a{};
@@ -240,7 +240,7 @@ int emu_steps_chained(mapc_posvelo *state, int n, int steps, float dt, float dam
         for (int i = 0; i < n; ++i) packed[sd][i] = make_float4(state[i].pos[0], state[i].pos[1], state[i].pos[2], state[i].pos[3]);
     std::vector<float4> partial((size_t)n_iblocks * S * per_block);
     std::vector<unsigned> counters(n / 64 + 2, 0u), block_step(n / 64 + 2, 0u);
-    unsigned done[2] = {0, 0};
+    unsigned done[3] = {0, 0, 0};
     unsigned long long error_word[2] = {0, 0};
     int b = 0;   // write side; both sides start alike, the first step reads side 1
     for (int k = 0; k < steps; ++k, b ^= 1) {
