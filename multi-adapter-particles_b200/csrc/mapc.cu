@@ -480,7 +480,10 @@ struct mapc_compute {
     bool gather_pending[2] = {false, false};
 
     // "simulate ms" timer (Compute.cpp:445-446, D3D12GpuTimer.h:151-153)
-    static constexpr int kTimerSlots = 4;
+    // steps whose timer may be unresolved at once = how far the host may run ahead of the device before Simulate
+    // blocks: 32 steps keep the queue fed through host hiccups even when a step is 40 us (the reference's frame
+    // loop never blocks in Simulate at all, only on the consumer's throttle)
+    static constexpr int kTimerSlots = 32;
     static constexpr float kAverageOver = 20.f;
     cudaEvent_t t_begin[kTimerSlots] = {}, t_end[kTimerSlots] = {};
     bool t_pending[kTimerSlots] = {};

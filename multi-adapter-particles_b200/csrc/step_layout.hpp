@@ -27,9 +27,12 @@ struct Plan {
 // target lanes the last block leaves idle.  The shape changes neither the arithmetic nor its order
 // (only S does), so it is free to vary with N, the shard size and the device.
 struct Shape { int pairs, threads, minb; float efficiency; };
-constexpr Shape kShapes[7] = {{4, 256, 2, 0.775f}, {4, 128, 4, 0.764f}, {2, 128, 8, 0.749f},
+// (1,128) has no large-N measurement of its own: its figure is set from config 2 (N = 10,000), where it beats (1,64)
+// by 4 % (41.9 vs 43.8 us per chained step: half as many cells, so half the per-cell prologue, waits and atomics);
+// (1,256) is there for the A/B only (efficiency 0: never chosen unless forced).
+constexpr Shape kShapes[8] = {{4, 256, 2, 0.775f}, {4, 128, 4, 0.764f}, {2, 128, 8, 0.749f},
                               {2, 64, 8, 0.757f},  {1, 64, 16, 0.735f}, {1, 32, 32, 0.730f},
-                              {1, 128, 8, 0.0f}};   // (1,128): only when forced (A/B for small N)
+                              {1, 128, 8, 0.760f}, {1, 256, 4, 0.0f}};
 
 // S = mapc_plan_segments(n_sources); force_pairs / force_threads != 0 pin the shape (MAPC_PLAN_PAIRS / _THREADS)
 inline Plan make_plan(int n_targets, int S, int sm_count, int force_pairs, int force_threads)

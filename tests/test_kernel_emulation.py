@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 EMU_DIR = os.path.join(HERE, "emu")
 
 # (pairs per thread, threads per block) of csrc/force_shapes.inc
-SHAPES = [(4, 256), (4, 128), (2, 128), (2, 64), (1, 64), (1, 32), (1, 128)]
+SHAPES = [(4, 256), (4, 128), (2, 128), (2, 64), (1, 64), (1, 32), (1, 128), (1, 256)]
 
 
 @pytest.fixture(scope="module")
