@@ -21,18 +21,15 @@ struct Plan {
     int block_targets() const { return threads * 2 * pairs; }
 };
 
-// Launch shapes (P, T) with the fraction of the FP32 peak each reaches at large N (tools/ubench at S = 32,
-// profiles/r02_ubench_probes.txt): all sit on the same 73-78 % plateau, so at large N the choice matters little, while
-// at small N what decides is how evenly the cells fall on the 4 x SMs warp schedulers and how many
-// target lanes the last block leaves idle.  The shape changes neither the arithmetic nor its order
-// (only S does), so it is free to vary with N, the shard size and the device.
+// Launch shapes (P, T) with the fraction of the FP32 peak each reaches at large N, measured the way the headline is
+// (N = 262,144, L2 flushed between steps; profiles/r02_shape_variants.txt; the P = 1 shapes scaled from the batched
+// sweep at N = 131,072, profiles/r02_small_n_shapes.txt).  At large N (2,128) wins by 1.3 %; at small N what decides is
+// how many of the SMs' block slots the cells fill at all, then how evenly they fall on the 148 SMs x 4 warp
+// schedulers and how many target lanes the last block leaves idle: (1,128) is the fastest shape up to N ~ 12,000.
+// The shape changes neither the arithmetic nor its order, so it is free to vary with N, the shard size and the device.
 struct Shape { int pairs, threads, minb; float efficiency; };
-// (1,128) has no large-N measurement of its own: its figure is set from config 2 (N = 10,000), where it beats (1,64)
-// by 4 % (41.9 vs 43.8 us per chained step: half as many cells, so half the per-cell prologue, waits and atomics);
-// (1,256) is there for the A/B only (efficiency 0: never chosen unless forced).
-constexpr Shape kShapes[8] = {{4, 256, 2, 0.775f}, {4, 128, 4, 0.764f}, {2, 128, 8, 0.749f},
-                              {2, 64, 8, 0.757f},  {1, 64, 16, 0.735f}, {1, 32, 32, 0.730f},
-                              {1, 128, 8, 0.760f}, {1, 256, 4, 0.0f}};
+constexpr Shape kShapes[7] = {{4, 256, 2, 0.771f}, {4, 128, 4, 0.762f}, {2, 128, 8, 0.784f}, {2, 64, 16, 0.781f},
+                              {1, 128, 8, 0.724f}, {1, 64, 16, 0.716f}, {1, 32, 32, 0.721f}};
 
 // S = mapc_plan_segments(n_sources); force_pairs / force_threads != 0 pin the shape (MAPC_PLAN_PAIRS / _THREADS)
 inline Plan make_plan(int n_targets, int S, int sm_count, int force_pairs, int force_threads)
@@ -45,11 +42,15 @@ inline Plan make_plan(int n_targets, int S, int sm_count, int force_pairs, int f
         const int bx = (n_targets + per_block - 1) / per_block;
         if (bx == 0) continue;
         const double used = (double)n_targets / ((double)bx * per_block);            // busy target lanes
-        const double blocks_per_sm = (double)bx * S / sm_count;
+        const double cells = (double)bx * S;
+        const double blocks_per_sm = cells / sm_count;
         const double warps_per_smsp = blocks_per_sm * (sh.threads / 32) / 4.0;
         const double bal_block = blocks_per_sm / std::ceil(blocks_per_sm);
         const double bal_warp = warps_per_smsp / std::ceil(warps_per_smsp);
-        const float score = (float)(sh.efficiency * used * std::min(bal_block, bal_warp));
+        // a grid that does not even fill the resident block slots runs latency-bound: the plateau figure scales with
+        // the filled fraction (measured: (4,256) at N = 10,000 fills 0.54 of its slots and takes 2.2x the time of (1,128))
+        const double occupancy = std::min(1.0, cells / ((double)sm_count * sh.minb));
+        const float score = (float)(sh.efficiency * used * std::min(bal_block, bal_warp) * occupancy);
         if (score > best_score) {
             best_score = score;
             best = Plan{sh.pairs, sh.threads, bx, S, sh.minb};

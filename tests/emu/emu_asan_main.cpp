@@ -20,7 +20,7 @@ extern "C" int emu_init_particles(void *side_a, void *side_b, float *packed_a, f
 extern "C" int emu_step_well(const void *in, void *out, float *pos_next_out, float *packed_out, int n,
                   int n_active, float dt, float damping, int i_first, int n_local);
 int main() {
-    const int shapes[8][2] = {{4,256},{4,128},{2,128},{2,64},{1,64},{1,32},{1,128},{1,256}};
+    const int shapes[7][2] = {{4,256},{4,128},{2,128},{2,64},{1,128},{1,64},{1,32}};
     int runs = 0;
     for (int n : {1, 65, 1000, 1100, 2048}) {
         std::vector<PV> in(n), out(n); std::vector<float> mirror(4*n), packed(4*n);

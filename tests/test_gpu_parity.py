@@ -254,7 +254,7 @@ def test_launch_geometry_does_not_change_bits(mapc, gpu):
             os.environ["MAPC_PLAN_PAIRS"], os.environ["MAPC_PLAN_THREADS"] = str(pairs), str(threads)
             assert gpu_steps(mapc, p, 2).tobytes() == base.tobytes(), ("TMA", pairs, threads)
         os.environ.pop("MAPC_TMA")
-        for pairs, threads in ((4, 256), (4, 128), (2, 128), (2, 64), (1, 64), (1, 32), (1, 128), (1, 256)):
+        for pairs, threads in ((4, 256), (4, 128), (2, 128), (2, 64), (1, 128), (1, 64), (1, 32)):
             os.environ["MAPC_PLAN_PAIRS"], os.environ["MAPC_PLAN_THREADS"] = str(pairs), str(threads)
             with mapc.Compute(n, 0) as c:
                 plan = c.Plan()
@@ -528,7 +528,7 @@ def test_chained_steps_are_bit_identical_to_grid_wide_waits(mapc, gpu):
         assert run(1).tobytes() == ref.tobytes(), (n, "single calls")
         assert run(7).tobytes() == ref.tobytes(), (n, "batches of 7")
         try:
-            for pairs, threads in ((1, 32), (1, 64), (1, 128), (1, 256), (2, 64), (2, 128), (4, 128)):
+            for pairs, threads in ((1, 32), (1, 64), (1, 128), (2, 64), (2, 128), (4, 128)):
                 os.environ["MAPC_PLAN_PAIRS"], os.environ["MAPC_PLAN_THREADS"] = str(pairs), str(threads)
                 assert run(30, 60).tobytes() == run(1, 60).tobytes(), (n, pairs, threads)
         finally:

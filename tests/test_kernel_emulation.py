@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 EMU_DIR = os.path.join(HERE, "emu")
 
 # (pairs per thread, threads per block) of csrc/force_shapes.inc
-SHAPES = [(4, 256), (4, 128), (2, 128), (2, 64), (1, 64), (1, 32), (1, 128), (1, 256)]
+SHAPES = [(4, 256), (4, 128), (2, 128), (2, 64), (1, 128), (1, 64), (1, 32)]
 
 
 @pytest.fixture(scope="module")
@@ -351,10 +351,14 @@ def test_launch_plan_and_dispatch_granularity(emu, oracle, mapc):
         emu.emu_make_plan(n_targets, S, sms, force[0], force[1], out)
         return tuple(out)
 
-    # config 3: 262,144 targets, S = 32 -> (4, 256), 128 target blocks x 32 segments = 4,096 cells
-    assert plan(262_144, 32) == (4, 256, 128, 32)
-    # an 8-GPU shard of config 5 (4,194,304 / 8 targets): 256 target blocks of (4, 256)
-    assert plan(524_288, 32) == (4, 256, 256, 32)
+    # config 3: 262,144 targets, S = 32 -> (2, 128), 512 target blocks x 32 segments = 16,384 cells
+    assert plan(262_144, 32) == (2, 128, 512, 32)
+    # an 8-GPU shard of config 5 (4,194,304 / 8 targets): 1,024 target blocks of (2, 128)
+    assert plan(524_288, 32) == (2, 128, 1024, 32)
+    # config 2: 10,000 targets fill the block slots only with a small shape -> (1, 128), 40 target blocks
+    assert plan(10_000, 32) == (1, 128, 40, 32)
+    # a size whose cells would leave most block slots of a big shape empty never gets that shape
+    assert plan(4_096, 32)[:2] in ((1, 128), (1, 64))
     # every shape can be forced, and covers all targets
     for pairs, threads in SHAPES:
         pl = plan(10_000, 32, (pairs, threads))

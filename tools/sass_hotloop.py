@@ -4,7 +4,7 @@
     python tools/sass_hotloop.py [P T] > profiles/r02_sass_force_default.txt
 
 Runs `cuobjdump -sass` on lib/libmapc.so, picks the fused, non-peer, default-staging instantiation of the
-launch shape (P, T) (default: 4 256, the shape the bench workload runs), finds its innermost hot loop -- the
+launch shape (P, T) (default: 2 128, the shape the bench workload runs), finds its innermost hot loop -- the
 backward branch whose body holds the most FFMA2 -- and prints an opcode histogram of that loop, how many of
 its 3-operand FFMA2 carry a `.reuse` flag, and the loop's SASS.  No GPU needed.
 """
@@ -19,7 +19,7 @@ LIB = os.path.join(ROOT, "multi-adapter-particles_b200", "lib", "libmapc.so")
 
 
 def main():
-    P, T = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) >= 3 else (4, 256)
+    P, T = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) >= 3 else (2, 128)
     sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
     funcs = re.split(r"\n\s*Function : ", sass)[1:]
     want = re.compile(rf"force_cells_kernelILi{P}ELi{T}ELi\d+ELi\d+ELi\d+ELi\d+ELb1ELb0ELb0ELb0ELb0ELi2048E")
