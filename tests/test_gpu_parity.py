@@ -289,26 +289,43 @@ def test_errors_are_loud(mapc, gpu):
 
 
 def test_gpu_timer_and_launch_counter(mapc, gpu):
+    """"simulate ms" (Compute.cpp:445-446): the in-kernel %globaltimer stamps and the cudaEvent pairs time the same
+    launches when steps wait for the whole previous grid (MAPC_CHAIN=0).  Chained steps overlap, so their timer runs
+    from the previous step's end stamp -- a per-step time that can only be shorter, never longer."""
     n = 4096
-    with mapc.Compute(n, 0) as c:
-        c.Upload(gentle_sphere(mapc, n, seed=3))
-        before = c.KernelLaunches()
-        for _ in range(8):
-            c.Simulate(n, 0)
-        c.WaitForGpu()
-        assert c.KernelLaunches() == before + 8       # one fused force+integrate kernel per step
-        times, last_ms = c.GetGpuTimes()
-        assert times[0][1] == "simulate ms" and times[0][0] > 0 and last_ms > 0
-        stamped = float(np.median(c.StepTimes()))      # in-kernel %globaltimer stamps (default)
+
+    def stamped_median(chain):
         try:
-            os.environ["MAPC_TIMER_EVENTS"] = "1"       # the same timer through cudaEvent pairs
+            os.environ["MAPC_CHAIN"] = "1" if chain else "0"
+            with mapc.Compute(n, 0) as c:
+                c.Upload(gentle_sphere(mapc, n, seed=3))
+                before = c.KernelLaunches()
+                for _ in range(8):
+                    c.Simulate(n, 0)
+                c.WaitForGpu()
+                assert c.KernelLaunches() == before + 8       # one fused force+integrate kernel per step
+                times, last_ms = c.GetGpuTimes()
+                assert times[0][1] == "simulate ms" and times[0][0] > 0 and last_ms > 0
+                samples = c.StepTimes()
+                assert samples.size == 8 and samples.min() > 0
+                return float(np.median(samples))
+        finally:
+            os.environ.pop("MAPC_CHAIN", None)
+
+    stamped = stamped_median(chain=False)              # in-kernel %globaltimer stamps (default timer)
+    try:
+        os.environ["MAPC_TIMER_EVENTS"] = "1"          # the same timer through cudaEvent pairs
+        with mapc.Compute(n, 0) as c:
+            c.Upload(gentle_sphere(mapc, n, seed=3))
             for _ in range(8):
                 c.Simulate(n, 0)
             c.WaitForGpu()
             events = float(np.median(c.StepTimes()))
-        finally:
-            os.environ.pop("MAPC_TIMER_EVENTS", None)
-        assert abs(stamped - events) <= 0.15 * events + 0.004, (stamped, events)
+    finally:
+        os.environ.pop("MAPC_TIMER_EVENTS", None)
+    assert abs(stamped - events) <= 0.15 * events + 0.004, (stamped, events)
+    chained = stamped_median(chain=True)
+    assert 0 < chained <= 1.05 * stamped + 0.002, (chained, stamped)
 
 
 def test_init_particles_equals_oracle_restatement(mapc, oracle, gpu):
