@@ -323,9 +323,9 @@ def test_gpu_timer_and_launch_counter(mapc, gpu):
             events = float(np.median(c.StepTimes()))
     finally:
         os.environ.pop("MAPC_TIMER_EVENTS", None)
-    assert abs(stamped - events) <= 0.15 * events + 0.004, (stamped, events)
+    assert abs(stamped - events) <= 0.25 * events + 0.006, (stamped, events)
     chained = stamped_median(chain=True)
-    assert 0 < chained <= 1.05 * stamped + 0.002, (chained, stamped)
+    assert 0 < chained <= 1.10 * stamped + 0.004, (chained, stamped)
 
 
 def test_init_particles_equals_oracle_restatement(mapc, oracle, gpu):
