@@ -615,9 +615,8 @@ mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::Step
         if (shfl) return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false, kAlt>(c, args, stream); \
         return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false>(c, args, stream);             \
     }
-    // unroll / order / blocks-per-SM per shape from the fused kernel measured in the library at N = 262,144
-    // (the unfused tools/ubench sweep ranks (4,256) U=2 op-major first, 77.3 %, but fused it is 24.67 ms
-    // against 24.04 ms for U=8 pair-major; profiles/r01_ubench_shapes_11op.txt, r01_shapes_in_library.txt)
+    // unroll / order / stage / blocks-per-SM per shape: the winners of sweeps of the FUSED kernel inside the library
+    // (csrc/force_shapes.inc, profiles/r02_shape_variants.txt) -- an unfused tools/ubench ranking does not carry over
 #include "force_shapes.inc"
 #undef MAPC_SHAPE
     return fail(MAPC_ERR_INVALID_ARGUMENT, "no kernel for launch shape P=%d T=%d", pl.pairs, pl.threads);

@@ -75,7 +75,7 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 //   ai += r * s                      (:56)   3 FFMA2
 // MASS_IN_LOOP = false (default): the uniform factor g_fParticleMass is left out of the pair and
 // applied once to each segment partial instead (lever (i)): 11 instead of 12
-// FMA-pipe lane-ops per interaction, 76 % instead of 72 % of the FP32 peak.  Same formula; each term
+// FMA-pipe lane-ops per interaction, 77-78 % instead of 72 % of the FP32 peak.  Same formula; each term
 // loses one rounding, so results differ from the per-pair multiply by ~1 ulp per partial -- far inside
 // the 1e-5 tolerance; the oracle's MIRRORED flavour does the same, LITERAL keeps the shader's order.
 template <bool MASS_IN_LOOP>
@@ -374,15 +374,17 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
         segment_range(a.n_sources, a.S, seg, j0, j1);
         if (a.wait_prev) {
             // dataflow instead of a grid-wide wait: the previous step must have integrated this cell's own
-            // target block and the target blocks that hold the bodies of its source segment
-            if (tid == 0) {
+            // target block and the target blocks that hold the bodies of its source segment.  One thread per
+            // awaited block polls (the L2 round trips overlap), the barrier below joins them.
+            {
                 const unsigned want = a.step_id - 1u;
-                const unsigned long long t0 = global_timer_ns();
                 int first = j1 > j0 ? j0 / kBlockTargets : ib, last = j1 > j0 ? (j1 - 1) / kBlockTargets : ib;
                 if (last >= a.n_iblocks) last = a.n_iblocks - 1;   // sources past the dispatched targets are never rewritten
-                for (int tb = first - 1; tb <= last; ++tb) {
-                    const int blk = tb < first ? ib : tb;          // first pass: the own target block
+                // awaited blocks: index 0 = the own target block, 1.. = first..last
+                for (int w = tid; w <= last - first + 1; w += T) {
+                    const int blk = w == 0 ? ib : first + w - 1;
                     if (blk >= a.n_iblocks) continue;
+                    const unsigned long long t0 = global_timer_ns();
                     while ((int)(load_acquire_gpu(a.block_step + blk) - want) < 0) {
                         __nanosleep(64);
                         if (a.error_word != nullptr && global_timer_ns() - t0 > a.wait_timeout_ns) {

@@ -319,11 +319,11 @@ void mapo_step_allpairs_targets_chunked(const mapo_posvelo *in, int n_sources,
                                         const int *targets, int n_targets, float dt, float damping,
                                         int S, int chunk, int flavour, int threads, mapo_posvelo *out_targets)
 {
-    enum { CHUNK = 4096 };
-    float buf[3 * CHUNK];
-    int ids[CHUNK];
-    for (int base = 0; base < n_targets; base += CHUNK) {
-        const int cnt = (n_targets - base) < CHUNK ? (n_targets - base) : CHUNK;
+    enum { BATCH = 4096 };   /* targets per pass: bounds the scratch, has no effect on any sum */
+    float buf[3 * BATCH];
+    int ids[BATCH];
+    for (int base = 0; base < n_targets; base += BATCH) {
+        const int cnt = (n_targets - base) < BATCH ? (n_targets - base) : BATCH;
         for (int q = 0; q < cnt; ++q) ids[q] = targets ? targets[base + q] : base + q;
         mapo_accel_allpairs_chunked(in, n_sources, S, chunk, flavour, ids, cnt, buf, threads);
         for (int q = 0; q < cnt; ++q)

@@ -78,7 +78,7 @@ def test_well_step_bitwise_equals_numpy_transcription(oracle, mapc):
 
 
 def accel_segments_chunked(pos, i, S, chunk, segment_range):
-    """The bounded-chain order (oracle `chunk`, kernel flag CHUNK): a segment longer than `chunk` sources is
+    """The canonical chains (oracle `chunk`, kernel template parameter CHAIN): a segment longer than `chunk` sources is
     taken in consecutive chunks counted from its first source, each one sequential chain; the chunk sums are
     folded left to right into the segment's partial, the partials left to right into the total."""
     total = np.zeros(3, dtype=F)
