@@ -27,7 +27,8 @@ from . import dist, ic  # noqa: F401  (re-exported)
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libmapc.so")
+# MAPC_LIB_PATH: load another build of the library (A/B tools such as tools/sassprobe/force_sweep.py); default: in-tree
+LIB_PATH = os.environ.get("MAPC_LIB_PATH") or os.path.join(PKG_DIR, "lib", "libmapc.so")
 
 # constants carried over from the reference (include/mapc.h cites each)
 BLOCK_SIZE = 64
