@@ -18,11 +18,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "multi-adapter-particles_b200", "lib", "libmapc.so")
 
 
-def main():
-    P, T = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) >= 3 else (2, 128)
-    sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+def hot_loop(want, lib=LIB):
+    """(function name, [(address, text)] of the innermost backward-branch loop holding the most FFMA2) of the first
+    function of `lib` whose mangled name matches the regular expression `want`."""
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
     funcs = re.split(r"\n\s*Function : ", sass)[1:]
-    want = re.compile(rf"force_cells_kernelILi{P}ELi{T}ELi\d+ELi\d+ELi\d+ELi\d+ELb1ELb0ELb0ELb0ELb0ELi2048E")
+    want = re.compile(want)
     body = next(f for f in funcs if want.search(f.split("\n", 1)[0]))
     name = body.split("\n", 1)[0].strip()
     ins = []   # (address, text)
@@ -44,7 +45,12 @@ def main():
         n_ffma2 = sum(1 for _, x in loop if re.search(r"\bFFMA2\b", x))
         if best is None or n_ffma2 > best[0]:
             best = (n_ffma2, loop)
-    n_ffma2, loop = best
+    return name, best[1]
+
+
+def main():
+    P, T = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) >= 3 else (2, 128)
+    name, loop = hot_loop(rf"force_cells_kernelILi{P}ELi{T}ELi\d+ELi\d+ELi\d+ELi\d+ELb1ELb0ELb0ELb0ELb0ELi2048E")
     hist = collections.Counter()
     for _, x in loop:
         x = re.sub(r"^@!?U?P\d+\s+", "", x)
@@ -52,7 +58,8 @@ def main():
     acc = [x for _, x in loop if re.search(r"\bFFMA2\b", x)]
     reuse = sum(1 for x in acc if ".reuse" in x)
     print(f"# {name}")
-    print(f"# hot loop: {len(loop)} instructions, 0x{loop[0][0]:x} .. 0x{loop[-1][0]:x}")
+    print(f"# hot loop: {len(loop)} instructions, 0x{loop[0][0]:x} .. 0x{loop[-1][0]:x} (first instruction at offset "
+          f"0x{loop[0][0] % 128:x} of its 128-byte instruction line)")
     print("# opcode histogram: " + ", ".join(f"{k} {v}" for k, v in hist.most_common()))
     print(f"# FFMA2 with a .reuse operand: {reuse} of {len(acc)}")
     for a, x in loop:

@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+batch = int(sys.argv[3]) if len(sys.argv) > 3 else 1     # > 1: chained steps, SimulateSteps(n, batch) per call
 pkg = importlib.import_module("multi-adapter-particles_b200")
 pkg.load()
 p = pkg.ic.uniform_sphere(n, 8000.0 * (n / 262144.0) ** (1 / 3), seed=2)
@@ -20,9 +21,17 @@ with pkg.Compute(n, 0) as c:
     c.SimulateSteps(n, 2)
     c.WaitForGpu()
     c.StepTimes()
-    for _ in range(steps):
-        c.Simulate(n)
+    if batch > 1:
+        c.SimulateSteps(n, batch)
         c.WaitForGpu()
+        c.StepTimes()
+        for _ in range(0, steps, batch):
+            c.SimulateSteps(n, batch)
+        c.WaitForGpu()
+    else:
+        for _ in range(steps):
+            c.Simulate(n)
+            c.WaitForGpu()
     t = c.StepTimes()
     plan = c.Plan()
     out = c.Download()
