@@ -402,6 +402,7 @@ struct Switches {
     bool peer;          // MAPC_PEER=0: attached peer exchange not used
     bool peer_single;   // MAPC_PEER_SINGLE=1 (experimental): peer exchange as ONE grid, local cells first
     int plan_pairs, plan_threads;  // MAPC_PLAN_PAIRS / MAPC_PLAN_THREADS: force a launch shape (0 = choose)
+    int blocks_per_sm;  // MAPC_BLOCKS_PER_SM: resident blocks per SM of chained small-N steps (-1 = choose, 0 = no throttle)
 };
 
 Switches read_switches()
@@ -423,6 +424,7 @@ Switches read_switches()
     w.peer_single = env_int("MAPC_PEER_SINGLE", 0) != 0;
     w.plan_pairs = env_int("MAPC_PLAN_PAIRS", 0);
     w.plan_threads = env_int("MAPC_PLAN_THREADS", 0);
+    w.blocks_per_sm = env_int("MAPC_BLOCKS_PER_SM", -1);
     return w;
 }
 
@@ -558,17 +560,51 @@ void resolve_timers(mapc_compute *c, bool block)
 // grid = target blocks x segments of this launch, one cell per thread block, segment index fastest
 template <int P, int T, int TJ, int U, int MINB, int ORDER, bool FUSE, bool PEER, bool INLOOP, bool TMA,
           bool SHFL = false>
-mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream_t stream)
+mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream_t stream, int blocks_per_sm = 0)
 {
     auto kernel = mapc::force_cells_kernel<P, T, TJ, U, MINB, ORDER, FUSE, PEER, TMA, INLOOP, SHFL>;
     dim3 grid((unsigned)args.n_iblocks * (unsigned)args.segs.count, 1, 1);
+    // Occupancy throttle (mapc::throttle_blocks_per_sm): at most `blocks_per_sm` blocks of this kernel are resident on
+    // an SM when every block also asks for dynamic shared memory it never touches.  The size that yields exactly k is
+    // found once per (instantiation, device, k) with the occupancy calculator.
+    size_t dyn_smem = 0;
+    if (blocks_per_sm > 0 && blocks_per_sm < MINB) {
+        constexpr int kMaxDev = 64;
+        static int dyn_for[kMaxDev][MINB] = {};     // bytes, 0 = not computed yet
+        static bool optin_done[kMaxDev] = {};
+        const int dev = c->device >= 0 && c->device < kMaxDev ? c->device : 0;
+        if (dyn_for[dev][blocks_per_sm] == 0) {
+            cudaFuncAttributes fa;
+            MAPC_CUDA(cudaFuncGetAttributes(&fa, kernel));
+            int per_sm = 0, reserved = 0, optin = 0;
+            MAPC_CUDA(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device));
+            MAPC_CUDA(cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, c->device));
+            MAPC_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+            const int most = optin - (int)fa.sharedSizeBytes;
+            if (!optin_done[dev]) {
+                MAPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+                optin_done[dev] = true;
+            }
+            int dyn = per_sm / blocks_per_sm - reserved - (int)fa.sharedSizeBytes;
+            dyn = std::max(1024, std::min(most, dyn / 1024 * 1024));
+            for (int tries = 0; tries < 64; ++tries) {   // settle on the largest size that still admits k blocks
+                int nb = 0;
+                MAPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, T, (size_t)dyn));
+                if (nb == blocks_per_sm || (nb < blocks_per_sm && dyn <= 1024) || (nb > blocks_per_sm && dyn >= most)) break;
+                dyn += nb > blocks_per_sm ? 1024 : -1024;
+                dyn = std::max(1024, std::min(most, dyn));
+            }
+            dyn_for[dev][blocks_per_sm] = dyn;
+        }
+        dyn_smem = (size_t)dyn_for[dev][blocks_per_sm];
+    }
     if (c->pdl_next) {
         // batched steps: the grid may be scheduled while the previous step's grid drains (the kernel
         // waits on griddepcontrol.wait before reading anything the previous step wrote)
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;
         cfg.blockDim = dim3(T, 1, 1);
-        cfg.dynamicSmemBytes = 0;
+        cfg.dynamicSmemBytes = dyn_smem;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -577,7 +613,7 @@ mapc_status launch_force(mapc_compute *c, const mapc::StepArgs &args, cudaStream
         cfg.numAttrs = 1;
         MAPC_CUDA(cudaLaunchKernelEx(&cfg, kernel, args));
     } else {
-        kernel<<<grid, T, 0, stream>>>(args);
+        kernel<<<grid, T, dyn_smem, stream>>>(args);
     }
     MAPC_CUDA(cudaGetLastError());
     ++c->launches;
@@ -594,14 +630,14 @@ enum Staging { kStageDefault = 0, kStageTma = 1, kStageShfl = 2 };
 
 template <bool FUSE, bool PEER = false, bool INLOOP = false>
 mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::StepArgs &args, cudaStream_t stream,
-                               Staging staging, int variant = 0)
+                               Staging staging, int variant = 0, int blocks_per_sm = 0)
 {
     if (args.segs.count == 0 || args.i_cnt <= 0) return MAPC_OK;
     if (FUSE && !PEER && !INLOOP && staging == kStageDefault && variant != 0) {
 #define MAPC_SHAPE(P, T, TJ, U, MINB, ORDER, HAS_TMA)
 #define MAPC_SHAPE_VARIANT(V, P, T, TJ, U, MINB, ORDER)                                         \
         if (variant == V && pl.pairs == P && pl.threads == T)                                   \
-            return launch_force<P, T, TJ, U, MINB, ORDER, FUSE && !PEER && !INLOOP, false, false, false>(c, args, stream);
+            return launch_force<P, T, TJ, U, MINB, ORDER, FUSE && !PEER && !INLOOP, false, false, false>(c, args, stream, blocks_per_sm);
 #include "force_shapes.inc"
 #undef MAPC_SHAPE_VARIANT
 #undef MAPC_SHAPE
@@ -613,7 +649,7 @@ mapc_status launch_force_shape(mapc_compute *c, const Plan &pl, const mapc::Step
     if (pl.pairs == P && pl.threads == T) {                                                                   \
         if (HAS_TMA && tma) return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, kAlt && HAS_TMA>(c, args, stream); \
         if (shfl) return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false, kAlt>(c, args, stream); \
-        return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false>(c, args, stream);             \
+        return launch_force<P, T, TJ, U, MINB, ORDER, FUSE, PEER, INLOOP, false>(c, args, stream, blocks_per_sm); \
     }
     // unroll / order / stage / blocks-per-SM per shape: the winners of sweeps of the FUSED kernel inside the library
     // (csrc/force_shapes.inc, profiles/r02_shape_variants.txt) -- an unfused tools/ubench ranking does not carry over
@@ -1171,9 +1207,13 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             // default once-per-partial scale (11): A/B switch, fused non-peer path only
             const bool inloop = fuse && sw.mass_in_loop;
             const Staging staging = sw.shfl ? kStageShfl : (sw.tma ? kStageTma : kStageDefault);
+            // steps that may chain by data flow run with fewer resident blocks per SM (mapc::throttle_blocks_per_sm)
+            const bool may_chain = publishes && !sc.ring && sw.chain && sw.pdl && staging == kStageDefault && !inloop;
+            const int throttle = !may_chain ? 0 : (sw.blocks_per_sm >= 0 ? sw.blocks_per_sm
+                                                                         : mapc::throttle_blocks_per_sm(pl, c->sm_count));
             auto launch = [&](cudaStream_t st) -> mapc_status {
                 if (inloop) return launch_force_shape<true, false, true>(c, pl, args, st, staging);
-                return fuse ? launch_force_shape<true>(c, pl, args, st, staging, sw.shape_variant)
+                return fuse ? launch_force_shape<true>(c, pl, args, st, staging, sw.shape_variant, throttle)
                             : launch_force_shape<false>(c, pl, args, st, staging);
             };
             if (single_grid) {

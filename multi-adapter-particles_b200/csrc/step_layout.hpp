@@ -59,6 +59,23 @@ inline Plan make_plan(int n_targets, int S, int sm_count, int force_pairs, int f
     return best;
 }
 
+// Occupancy throttle of steps that chain by data flow (unsharded fused steps below the scratch-ring size, DESIGN.md
+// section 4).  Such a step cannot finish a single target block before the previous step has published its LAST one
+// (every target needs every source), so what bounds a run of small steps is how long a cell takes once its inputs are
+// there -- and a cell that shares its SM with seven others takes four times as long as one that shares it with one.
+// Fewer resident blocks per SM = the same throughput (the 8-source unroll of the P = 1 kernels keeps the FMA pipe fed
+// from 2-4 warps per scheduler) at a fraction of the latency.  Measured on B200 with the (1,128) shape, us per chained
+// step for 8 / best k resident blocks per SM (profiles/r02_small_n_occupancy.txt): N = 2,500 15.9 / 12.7 (k = 2),
+// 4,096 19.6 / 15.9 (3), 6,000 27.3 / 22.5 (4), 8,192 33.9 / 29.9 (4-5), 10,000 41.7 / 40.5 (6), >= 12,000 no gain (8):
+// the best k keeps about three quarters of a step's cells resident.  Returns 0 when the kernel's own occupancy is kept.
+inline int throttle_blocks_per_sm(const Plan &pl, int sm_count)
+{
+    const double cells = (double)pl.blocks_x * pl.segments;
+    int k = (int)std::floor(0.75 * cells / sm_count + 0.5);
+    if (k < 1) k = 1;
+    return k < pl.minb ? k : 0;
+}
+
 // targets of the shard [i_first, i_first + n_local) that a Simulate(n_active) updates, as a count from
 // i_first: Dispatch(ceil(n/64)) groups of 64 threads (Compute.cpp:1041); writes past N are dropped
 inline int local_targets(uint32_t n, uint32_t i_first, uint32_t n_local, int n_active)

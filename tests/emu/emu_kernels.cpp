@@ -325,6 +325,12 @@ void emu_make_plan(int n_targets, int S, int sm_count, int force_pairs, int forc
     out[0] = pl.pairs; out[1] = pl.threads; out[2] = pl.blocks_x; out[3] = pl.segments;
 }
 
+// csrc/step_layout.hpp throttle_blocks_per_sm for the plan make_plan picks: resident blocks per SM, 0 = kernel's own
+int emu_throttle_blocks_per_sm(int n_targets, int S, int sm_count, int force_pairs, int force_threads)
+{
+    return mapc::throttle_blocks_per_sm(mapc::make_plan(n_targets, S, sm_count, force_pairs, force_threads), sm_count);
+}
+
 int emu_local_targets(unsigned n, unsigned i_first, unsigned n_local, int n_active)
 {
     return mapc::local_targets(n, i_first, n_local, n_active);

@@ -516,6 +516,35 @@ def test_batched_steps_equal_single_steps(mapc, gpu):
         assert c.GetSharedHandles().m_bufferIndex == 1      # 7 steps: odd number of flips
 
 
+def test_occupancy_throttle_does_not_change_bits(mapc, gpu):
+    """Chained small-N steps run with fewer resident blocks per SM than the kernel allows (unused dynamic shared
+    memory, csrc/step_layout.hpp throttle_blocks_per_sm): a cell that shares its SM with fewer others publishes its
+    target block sooner.  Only residency changes -- the bytes after 90 steps must equal those of the unthrottled
+    run for the library's own choice and for every forced value, batched and as single calls."""
+    for n, seed in ((6_000, 5), (10_000, 6), (1_000, 7)):
+        p = mapc.ic.uniform_sphere(n, 2000.0 * (n / 10_000.0) ** (1 / 3), seed, speed=1.0)
+
+        def run(batch, steps=90):
+            with mapc.Compute(n, 0) as c:
+                c.Upload(p)
+                for k in range(0, steps, batch):
+                    c.SimulateSteps(n, min(batch, steps - k))
+                c.WaitForGpu()
+                return c.Download()
+
+        try:
+            os.environ["MAPC_BLOCKS_PER_SM"] = "0"
+            ref = run(30)
+            for k in ("1", "2", "3", "5", "7"):
+                os.environ["MAPC_BLOCKS_PER_SM"] = k
+                assert run(30).tobytes() == ref.tobytes(), (n, k)
+            os.environ["MAPC_BLOCKS_PER_SM"] = "2"
+            assert run(1, 40).tobytes() == run(40, 40).tobytes(), (n, "single calls")
+        finally:
+            os.environ.pop("MAPC_BLOCKS_PER_SM", None)
+        assert run(30).tobytes() == ref.tobytes(), (n, "library's own choice")
+
+
 def test_chained_steps_are_bit_identical_to_grid_wide_waits(mapc, gpu):
     """Consecutive small-N steps are chained by per-target-block flags (a cell waits only for the blocks of the
     previous step it reads) instead of waiting for the whole previous grid.  Same cells, same

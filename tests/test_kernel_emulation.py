@@ -365,6 +365,13 @@ def test_launch_plan_and_dispatch_granularity(emu, oracle, mapc):
         assert pl[:2] == (pairs, threads) and pl[2] * pairs * 2 * threads >= 10_000 > (pl[2] - 1) * pairs * 2 * threads
     # a single target still gets a block
     assert plan(1, 32)[2] == 1
+    # occupancy throttle of chained small-N steps: about three quarters of a step's cells resident, never more blocks
+    # per SM than the kernel is compiled for (0 = no throttle), the measured optimum at the sizes that were swept
+    # (profiles/r02_small_n_occupancy.txt)
+    emu.emu_throttle_blocks_per_sm.restype = ctypes.c_int
+    emu.emu_throttle_blocks_per_sm.argtypes = [ctypes.c_int] * 5
+    throttle = {n: emu.emu_throttle_blocks_per_sm(n, 32, 148, 1, 128) for n in (1_000, 2_500, 4_096, 6_000, 8_192, 10_000, 12_000, 16_384)}
+    assert throttle == {1_000: 1, 2_500: 2, 4_096: 3, 6_000: 4, 8_192: 5, 10_000: 6, 12_000: 0, 16_384: 0}
     # dispatch granularity (Compute.cpp:1041) agrees with the oracle's statement of it
     for n, n_active in ((1000, 0), (1000, 1), (1000, 64), (1000, 65), (1000, 999), (1000, 1000), (10_000, 9_999)):
         assert emu.emu_local_targets(n, 0, n, n_active) == oracle.num_targets(n, n_active)
