@@ -391,6 +391,7 @@ struct Switches {
     bool pdl;           // MAPC_PDL=0: no programmatic dependent launch between consecutive steps
     bool tma;           // MAPC_TMA=1: cp.async.bulk source staging instead of LDG/STS
     bool shfl;          // MAPC_SHFL=1: warp-shuffle broadcast of staged sources instead of LDS broadcast
+    bool ring_group;    // MAPC_RING_GROUP=0: ring cells in target-block-major order instead of segment-major groups
     bool ring;          // MAPC_RING=0: every target block its own scratch slot (no L2-resident ring)
     int shape_variant;  // MAPC_SHAPE_VARIANT=v: A/B instantiations of the large-N shapes (csrc/force_shapes.inc)
     bool chain;         // MAPC_CHAIN=0: consecutive small-N steps wait for the whole previous grid, not per target block
@@ -413,6 +414,7 @@ Switches read_switches()
     w.tma = env_int("MAPC_TMA", 0) != 0;
     w.shfl = env_int("MAPC_SHFL", 0) != 0;
     w.ring = env_int("MAPC_RING", 1) != 0;
+    w.ring_group = env_int("MAPC_RING_GROUP", 1) != 0;
     w.chain = env_int("MAPC_CHAIN", 1) != 0;
     w.shape_variant = env_int("MAPC_SHAPE_VARIANT", 0);
     w.wait_timeout_ms = env_int("MAPC_WAIT_TIMEOUT_MS", 20000);
@@ -1147,6 +1149,9 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             args.pos = c->packed[r];
             args.partial = c->partial;
             args.scratch_blocks = sc.slots;
+            // grouped cell order (MAPC_RING_GROUP=0: target block major): half the ring per group, so that a cell only
+            // ever waits for a target block two groups back
+            args.group_blocks = (sc.ring && sw.ring_group && sc.slots >= 4) ? sc.slots / 2 : 0;
             args.ticket = sc.ring ? c->done + 1 : nullptr;
             args.slot_gen = sc.ring ? c->slot_gen : nullptr;
             args.i_first = (int)c->i_first;

@@ -174,6 +174,7 @@ struct StepArgs {
     // counter in (target block, segment) order, so every cell a block can wait for is already running.
     float4 *partial;
     int scratch_blocks;
+    int group_blocks;          // > 0 (ring only): tickets map to cells in groups of this many target blocks, segment major inside
     unsigned *ticket;          // next cell of this launch, or null: cell = blockIdx.x
     unsigned *slot_gen;        // [scratch_blocks] target blocks combined out of each slot this step, or null
     int i_first, i_cnt;        // local targets are bodies [i_first, i_first + i_cnt)
@@ -360,7 +361,24 @@ __global__ void __launch_bounds__(T, MINB) force_cells_kernel(const __grid_const
     if (!a.wait_prev) pdl_wait();
     unsigned cell = blockIdx.x;
     if (a.ticket != nullptr) {
-        if (tid == 0) s_cell = atomicAdd(a.ticket, 1u);
+        if (tid == 0) {
+            // Tickets are handed out in an order of their own (a.group_blocks > 0): groups of `group_blocks` target
+            // blocks, and inside a group SEGMENT major -- cells that run side by side then read the SAME source segment,
+            // so at sizes whose positions exceed the L2 (N = 4 M: 67 MB) a segment is fetched from HBM once per group
+            // instead of once per target block.  Any bijection is legal: a partial depends on (target, segment) only,
+            // and a ticket still precedes every ticket it can wait for (the target block two groups earlier).
+            unsigned t = atomicAdd(a.ticket, 1u);
+            if (a.group_blocks > 0) {
+                const unsigned count = (unsigned)a.segs.count, per_group = (unsigned)a.group_blocks * count;
+                const unsigned g = t / per_group, r = t - g * per_group;
+                const unsigned first = g * (unsigned)a.group_blocks;
+                const unsigned left = (unsigned)a.n_iblocks - first;
+                const unsigned nb = left < (unsigned)a.group_blocks ? left : (unsigned)a.group_blocks;   // a short last group
+                const unsigned kseg = r / nb;
+                t = (first + (r - kseg * nb)) * count + kseg;
+            }
+            s_cell = t;
+        }
         __syncthreads();
         cell = s_cell;
     }

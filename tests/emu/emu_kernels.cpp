@@ -135,6 +135,7 @@ int emu_step_allpairs(const mapc_posvelo *in, mapc_posvelo *out, float *pos_next
         a.pos = packed[r].data();
         a.partial = partial.data();
         a.scratch_blocks = slots;
+        a.group_blocks = (ring && slots >= 4) ? slots / 2 : 0;    // like csrc/mapc.cu
         a.ticket = ring ? &done[1] : nullptr;
         a.slot_gen = ring ? slot_gen.data() : nullptr;
         a.i_first = i_first;

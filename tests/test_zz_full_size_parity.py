@@ -42,13 +42,19 @@ def test_full_size_262144_one_step_all_targets(mapc, oracle, gpu):
     print("N=262,144, all targets, 1 step: global", err, "per-body", body)
     assert max(err.values()) <= TOL_1, err
     assert body["accel_rel_l2_p99"] <= TOL_1 and body["pos_ulp_max"] <= 2.0, body
-    # the scratch ring (the default at this size: 128 target blocks share 32 slots) changes no bit
+    # the scratch ring (the default at this size: 512 target blocks share 128 slots) changes no bit, and neither does
+    # the order its tickets map to cells (default: groups of 64 target blocks, segment major inside a group)
     import os
     try:
         os.environ["MAPC_RING"] = "0"
         assert gpu_steps(mapc, p, 1).tobytes() == got.tobytes()
     finally:
         os.environ.pop("MAPC_RING", None)
+    try:
+        os.environ["MAPC_RING_GROUP"] = "0"
+        assert gpu_steps(mapc, p, 1).tobytes() == got.tobytes()
+    finally:
+        os.environ.pop("MAPC_RING_GROUP", None)
 
 
 def test_full_size_262144_ten_steps_all_targets_lattice(mapc, oracle, gpu):
