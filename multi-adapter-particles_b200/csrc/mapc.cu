@@ -1134,6 +1134,9 @@ static mapc_status enqueue_one(mapc_compute *c, uint32_t b, int n_targets, int n
             ++c->launches;
         } else {
             const Plan pl = make_plan(n_targets, n_sources, c->sm_count, sw);
+            if (pl.blocks_x <= 0)
+                return fail(MAPC_ERR_INVALID_ARGUMENT, "MAPC_PLAN_PAIRS=%d MAPC_PLAN_THREADS=%d name no launch shape "
+                            "(csrc/force_shapes.inc)", sw.plan_pairs, sw.plan_threads);
             const bool fuse = sw.fuse;
             // scratch ring (stays in L2) for unsharded fused steps; everything else one slot per target block
             const mapc::Scratch sc = mapc::plan_scratch(pl, c->sm_count, c->world == 1 && fuse && sw.ring);

@@ -516,6 +516,25 @@ def test_batched_steps_equal_single_steps(mapc, gpu):
         assert c.GetSharedHandles().m_bufferIndex == 1      # 7 steps: odd number of flips
 
 
+def test_forced_launch_shape_that_does_not_exist_is_refused(mapc, gpu):
+    """MAPC_PLAN_PAIRS / MAPC_PLAN_THREADS naming a shape csrc/force_shapes.inc does not hold: an error, not an empty launch."""
+    p = mapc.ic.uniform_sphere(2048, 500.0, 3)
+    try:
+        os.environ["MAPC_PLAN_PAIRS"], os.environ["MAPC_PLAN_THREADS"] = "3", "96"
+        with mapc.Compute(2048, 0) as c:
+            c.Upload(p)
+            with pytest.raises(mapc.MapcError) as e:
+                c.Simulate(2048, 0)
+            assert "no launch shape" in str(e.value)
+    finally:
+        os.environ.pop("MAPC_PLAN_PAIRS", None)
+        os.environ.pop("MAPC_PLAN_THREADS", None)
+    with mapc.Compute(2048, 0) as c:      # and the handle-independent state is unharmed
+        c.Upload(p)
+        c.Simulate(2048, 0)
+        c.WaitForGpu()
+
+
 def test_occupancy_throttle_does_not_change_bits(mapc, gpu):
     """Chained small-N steps run with fewer resident blocks per SM than the kernel allows (unused dynamic shared
     memory, csrc/step_layout.hpp throttle_blocks_per_sm): a cell that shares its SM with fewer others publishes its

@@ -12,7 +12,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-SHAPES = [(4, 256), (4, 128), (2, 128), (2, 64), (1, 256), (1, 128), (1, 64), (1, 32)]
+SHAPES = [(4, 256), (4, 128), (2, 128), (2, 64), (1, 128), (1, 64), (1, 32)]
 SIZES = [1000, 2500, 4096, 6000, 8192, 10_000, 16_384, 24_576, 32_768, 65_536, 131_072]
 
 
