@@ -40,6 +40,13 @@ int main() {
                     if (rc != 0) { printf("rc %d n %d S %d variant %d\n", rc, n, S, variant); return 1; }
                     ++runs;
                 }
+        // rings of 4+ slots: tickets map to cells in segment-major groups of slots/2 target blocks (short last group)
+        for (int ring : {4, 5, 8})
+            for (int order : {0, 1}) {
+                int rc = emu_step_allpairs(in.data(), out.data(), mirror.data(), n, n, 0.1f, 1.f, 32, 1, 32, 1, 0, 1, 0, order, 2048, 0, ring, info);
+                if (rc != 0) { printf("ring rc %d n %d ring %d\n", rc, n, ring); return 1; }
+                ++runs;
+            }
         emu_step_well(in.data(), out.data(), mirror.data(), packed.data(), n, n, 0.1f, 1.f, 0, n);
         // chained steps (per-target-block flags) and the initial-conditions kernel, exactly-sized buffers
         for (auto &sh : shapes) {
