@@ -420,7 +420,7 @@ def test_fuzz_emulated_kernel_against_oracle(emu, oracle, mapc):
     @settings(max_examples=150, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
     @given(n=st.integers(1, 700), S=st.integers(1, 32), shape=st.sampled_from(SHAPES),
            frac=st.floats(0.0, 1.0), fuse=st.booleans(), chunk=st.sampled_from([CHAIN, CHAIN, 256]),
-           ring=st.sampled_from([0, 0, 1, 2, 5]), seed=st.integers(0, 1000))
+           ring=st.sampled_from([0, 0, 1, 2, 4, 5, 8]), seed=st.integers(0, 1000))
     def check(n, S, shape, frac, fuse, chunk, ring, seed):
         n_active = max(1, min(n, int(round(frac * n)))) if frac < 0.9 else n
         p = mapc.ic.uniform_sphere(n, 150.0, seed=seed, speed=1.0)
