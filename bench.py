@@ -22,6 +22,8 @@ every run adds to the same line, each a short leg of its own:
   well         the step the reference actually dispatches (CSMain, nBodyGravityCS.hlsl:86-109) at the
                reference's default N = 4,194,304 (defines.h:45) as an HBM-bound kernel: GB/s against the
                measured copy peak (1 GPU runs only; `--mode well` makes it the headline instead)
+  latency      BASELINE config 2: microseconds per step of a 1,000-step ping-pong run at N = 10,000 issued in batches
+               of 50 (1 GPU runs only; `--bodies 10000 --batch 50` makes it the headline instead)
   cpu_baseline.parity   the GPU result of the headline workload against the oracle (LITERAL) and the fp64
                direct sum on a target sample -- a fast wrong kernel would show here
 """
@@ -381,6 +383,33 @@ def determinism_leg(h: Harness) -> dict:
                     "across --gpus 1/2/4/8 = bit-identical results"}
 
 
+LATENCY_N = 10_000
+
+
+def latency_leg(h: Harness, steps: int = 1000, batch: int = 50) -> dict:
+    """BASELINE config 2 inside the default line: microseconds per step of a 1,000-step ping-pong run at N = 10,000
+    (the same constant-density uniform sphere, issued in batches of 50: steps chained per target block, occupancy
+    throttle -- DESIGN.md section 4).  Timed like the headline (CUDA events on the compute stream around exactly
+    `steps` steps, no L2 flush: the state is 0.6 MB).  One GPU only: a sharded handle does not chain steps.
+    Never fatal: a failure is reported in the leg instead of costing the line."""
+    try:
+        pkg = h.pkg
+        n = LATENCY_N
+        c = h.compute(n)
+        c.Upload(make_particles(pkg, n))
+        plan = c.Plan()
+        ms, step_ms, launches, _ = h.timed_steps(c, n, steps, 50, flush=False, batch=batch)
+        c.close()
+        out = {"workload": f"allpairs uniform sphere N={n} seed={SEED}", "n": n, "steps": steps, "batch": batch,
+               "us_per_step": ms * 1e3, "plan": plan, "gpu_launches": launches}
+        if step_ms.size:
+            out["kernel_us_per_step_median"] = float(np.median(step_ms)) * 1e3
+        out["g_interactions_per_s"] = float(n) * float(n) / (ms * 1e-3) / 1e9
+        return out
+    except Exception as e:   # noqa: BLE001  (a latency leg must not take the headline down with it)
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def well_leg(h: Harness, n: int, steps: int = 20, warmup: int = 5) -> dict:
     """The kernel the reference dispatches (CSMain: gravity well + integration, nBodyGravityCS.hlsl:86-109) as
     an HBM-bound kernel: 80 B per body (32 B PosVelo in, 32 B out, 16 B packed mirror).  Per-launch times are
@@ -461,6 +490,11 @@ def run_mapc(args) -> None:
                               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                               "data": "synthetic", "config": {"workload": f"well (CSMain as shipped) two shells N={n}", "l2": w["l2"]},
                               "roofline": w["roofline"], "gpu_launches": w["gpu_launches"]}), flush=True)
+        return
+
+    if args.latency_leg_only:
+        if rank == 0:
+            print(json.dumps({"latency": latency_leg(h)}), flush=True)
         return
 
     n = workload_n(pkg, world, args.scaling, args.n)
@@ -556,6 +590,7 @@ def run_mapc(args) -> None:
             legs["config4"] = strong_leg(h, CONFIG4_N, "sphere_1048576", steps=10, warmup=3)
         if world == 1:
             legs["well"] = well_leg(h, STRONG_N)
+            legs["latency"] = latency_leg(h)
 
     line = None
     if rank == 0:
@@ -619,6 +654,7 @@ def main() -> None:
                     help="well: the reference's shipped CSMain step (HBM-bound) at N = 4,194,304 as the headline")
     ap.add_argument("--headline-only", action="store_true",
                     help="skip the strong-scaling / determinism / well legs (profiling and latency runs)")
+    ap.add_argument("--latency-leg-only", action="store_true", help="print only the config-2 latency leg (N = 10,000)")
     ap.add_argument("--strong-steps", type=int, default=3, help="timed steps of the N = 4,194,304 strong-scaling leg")
     args = ap.parse_args()
     if args.warmup < 3:
